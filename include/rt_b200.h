@@ -1,0 +1,201 @@
+/*
+ * rt_b200.h — C-ABI of the B200-native Whitted hot path.
+ *
+ * This is the drop-in boundary for the per-pixel path of the CENG477 ray tracer
+ * (reference: raytracer.cpp:335 `RayTracer::RayTracer(parser::Scene&)` and
+ * raytracer.cpp:362 `Image RayTracer::render(Camera&)`; the post step
+ * raytracer.cpp:459 `ImageProcessor::downSample` is fused into rt_render).
+ * Plain pointers and sizes only; nothing throws across this boundary.
+ *
+ * All arrays are caller-owned, read-only and may be freed as soon as the call
+ * returns.  Ids are 1-based exactly as in the reference's scene files
+ * (parser.h:194-204).  There is no CPU fallback: every entry point that needs a
+ * GPU returns RT_ERR_CUDA when none is usable.
+ */
+#ifndef RT_B200_H
+#define RT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_B200_ABI_VERSION 1
+
+/* error codes (0 = success, negative = failure; text via rt_last_error()) */
+#define RT_OK 0
+#define RT_ERR_INVALID (-1) /* null pointer, bad id, bad size */
+#define RT_ERR_CUDA (-2)    /* CUDA runtime error or no device */
+#define RT_ERR_NOMEM (-3)
+#define RT_ERR_STATE (-4) /* handle used on the wrong device / busy */
+
+/* parser.h:18-20 Vec3f */
+typedef struct RtVec3 {
+  float x, y, z;
+} RtVec3;
+
+/* parser.h:185-192 Material (is_mirror <- `type="mirror"`, parser.cpp:119) */
+typedef struct RtMaterial {
+  RtVec3 ambient;
+  RtVec3 diffuse;
+  RtVec3 specular;
+  RtVec3 mirror;
+  float phong_exponent;
+  int32_t is_mirror;
+} RtMaterial;
+
+/* parser.h:180-183 PointLight */
+typedef struct RtPointLight {
+  RtVec3 position;
+  RtVec3 intensity;
+} RtPointLight;
+
+/* parser.h:243-251 Triangle: the flat list the reference builds at
+ * raytracer.cpp:336-341 — every <Triangle> first, then each mesh's faces in
+ * file order, the mesh's material copied onto each face. */
+typedef struct RtTriangle {
+  int32_t v0_id, v1_id, v2_id; /* 1-based into vertices */
+  int32_t material_id;         /* 1-based into materials */
+} RtTriangle;
+
+/* parser.h:200-204 Sphere */
+typedef struct RtSphere {
+  int32_t material_id;
+  int32_t center_vertex_id;
+  float radius;
+} RtSphere;
+
+/* parser.h:254-266 Scene, flattened */
+typedef struct RtSceneDesc {
+  const RtVec3 *vertices;
+  int32_t n_vertices;
+  const RtTriangle *triangles;
+  int32_t n_triangles;
+  const RtSphere *spheres;
+  int32_t n_spheres;
+  const RtMaterial *materials;
+  int32_t n_materials;
+  const RtPointLight *lights;
+  int32_t n_lights;
+  RtVec3 ambient_light;
+  int32_t background[3]; /* parser.cpp:33 — parsed as ints */
+  float shadow_ray_epsilon;
+  int32_t max_recursion_depth;
+} RtSceneDesc;
+
+/* parser.h:170-178 Camera (near_plane = l r b t); image_width/height are the
+ * OUTPUT resolution — the supersampling factor is an argument of rt_render,
+ * not pre-multiplied into the camera as raytracer.cpp:506-509 does. */
+typedef struct RtCamera {
+  RtVec3 position;
+  RtVec3 gaze;
+  RtVec3 up;
+  float l, r, b, t;
+  float near_distance;
+  int32_t image_width, image_height;
+} RtCamera;
+
+/* acceleration-structure builders (rt_scene_create) */
+#define RT_BUILD_DEFAULT 0
+#define RT_BUILD_LBVH_GPU 1 /* Morton + radix sort + Karras on the GPU */
+#define RT_BUILD_SAH_HOST 2 /* binned SAH on the host (quality yardstick) */
+
+typedef struct RtBuildOptions {
+  int32_t builder;    /* RT_BUILD_* */
+  int32_t brute_force; /* 1: ignore the BVH and test every primitive (parity debugging) */
+  int32_t reserved[6];
+} RtBuildOptions;
+
+/* counters are exact (device atomics); "ray" = one closest-hit query
+ * (raytracer.cpp:177) or one any-hit query (raytracer.cpp:227) */
+typedef struct RtStats {
+  uint64_t primary_rays;
+  uint64_t reflection_rays; /* reflection rays actually traced */
+  uint64_t shadow_rays;
+  uint64_t shadow_occluded;
+  float ms_render; /* device time of the render kernel(s), CUDA events */
+  float ms_d2h;    /* device-to-host copy of the RGB8 frame */
+  float ms_total;  /* camera known -> RGB8 on host */
+  int32_t n_launches; /* kernels launched by this call */
+  int32_t reserved[3];
+} RtStats;
+
+typedef struct RtSceneInfo {
+  int32_t n_triangles, n_spheres;
+  int32_t bvh_nodes;      /* nodes of the traversal BVH */
+  int32_t bvh_max_depth;
+  int32_t ref_tree_nodes; /* nodes of the reference-order tree (bvh.h:48-105) used for tie ranks */
+  int32_t ref_tree_leaves;
+  int32_t ref_tree_max_leaf;
+  int32_t ref_tree_max_depth;
+  float ms_build_host;   /* reference-order ranks + host staging */
+  float ms_build_device; /* device BVH build (CUDA events) */
+  float bvh_sah_cost;
+  int32_t builder;
+  int32_t device;
+  int32_t reserved[3];
+} RtSceneInfo;
+
+typedef struct RtScene RtScene; /* opaque */
+
+/* Replaces RayTracer::RayTracer (raytracer.cpp:335-350): stages the scene as
+ * SoA buffers in HBM on the CURRENT CUDA device, builds the BVH there and the
+ * reference-order tie ranks.  opts may be NULL. */
+int rt_scene_create(const RtSceneDesc *desc, const RtBuildOptions *opts, RtScene **out);
+void rt_scene_destroy(RtScene *scene);
+int rt_scene_info(const RtScene *scene, RtSceneInfo *info);
+
+/* Replaces RayTracer::render + ImageProcessor::downSample
+ * (raytracer.cpp:362-383, 459-484): renders `cam` at aa_factor x aa_factor
+ * regular-grid supersampling, each sub-sample quantised to 8 bits and the
+ * f*f samples averaged with truncating integer division, into caller-allocated
+ * HOST memory rgb_out[image_height][image_width][3] (top row first).
+ * Synchronous; one call at a time per handle.  stats may be NULL. */
+int rt_render(RtScene *scene, const RtCamera *cam, int aa_factor, unsigned char *rgb_out,
+              RtStats *stats);
+
+/* ---- multi-GPU: interleaved tiles, scene replicated per GPU ---------------
+ * The output image is cut into RT_TILE x RT_TILE pixel tiles, numbered
+ * row-major; tile k belongs to part (k % part_world).  This mirrors the
+ * reference's interleaved rows (raytracer.cpp:353) for load balance. */
+#define RT_TILE 32
+
+/* number of tiles part `part_rank` owns, and bytes of its packed tile buffer
+ * (n_tiles * RT_TILE * RT_TILE * 3; edge tiles are padded). */
+int64_t rt_part_tiles(const RtCamera *cam, int part_rank, int part_world);
+int64_t rt_part_bytes(const RtCamera *cam, int part_rank, int part_world);
+
+/* Renders only this part's tiles into DEVICE memory d_tiles (packed, tile-major,
+ * rt_part_bytes long) on `cuda_stream` (a cudaStream_t, may be NULL for the
+ * default stream).  Asynchronous w.r.t. the host unless stats != NULL. */
+int rt_render_part(RtScene *scene, const RtCamera *cam, int aa_factor, int part_rank,
+                   int part_world, void *d_tiles, void *cuda_stream, RtStats *stats);
+
+/* As rt_render_part, but each finished pixel is stored straight into a
+ * row-major RGB8 frame at d_frame (image_height*image_width*3 bytes), which
+ * may be peer memory of another GPU mapped into this process (NVLink P2P):
+ * the gather is fused into the render kernel's epilogue. */
+int rt_render_part_into_frame(RtScene *scene, const RtCamera *cam, int aa_factor, int part_rank,
+                              int part_world, void *d_frame, void *cuda_stream, RtStats *stats);
+
+/* On the gathering GPU: scatters `part_world` packed tile buffers laid out back
+ * to back with stride `part_stride_bytes` (>= the largest rt_part_bytes) into a
+ * row-major RGB8 frame d_frame. */
+int rt_assemble_tiles(const RtCamera *cam, int part_world, const void *d_parts,
+                      int64_t part_stride_bytes, void *d_frame, void *cuda_stream);
+
+/* Single-process multi-GPU convenience used by the `raytracer` CLI: one handle
+ * per device in scenes[0..n_gpus), tiles gathered to scenes[0]'s device with
+ * peer copies, one D2H. */
+int rt_render_multi(RtScene *const *scenes, int n_gpus, const RtCamera *cam, int aa_factor,
+                    unsigned char *rgb_out, RtStats *stats);
+
+const char *rt_last_error(void);
+int rt_abi_version(void);
+int rt_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_B200_H */

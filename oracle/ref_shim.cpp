@@ -1,0 +1,275 @@
+// oracle/ref_shim.cpp — TEST INFRASTRUCTURE, not product code.
+//
+// Thin C entry points around the UNMODIFIED reference renderer so that Python
+// (ctypes) can drive it: tests/golden/make_golden.py renders the golden images
+// with it, tests pin oracle/whitted_oracle.c against it, and
+// `bench.py --impl reference` times it.  No reference source is copied: the
+// translation unit below is compiled from where it lies (-I/root/reference, see
+// oracle/Makefile) and only the built library lands in oracle/_ref/.
+//
+// What is used of the reference, all public members (raytracer.cpp):
+//   parser::Scene::loadFromXml            parser.cpp:6
+//   RayTracer::RayTracer(Scene&)          raytracer.cpp:335   (BVH build)
+//   RayTracer::render(Camera&)            raytracer.cpp:362   (its own thread fan-out)
+//   ImageProcessor::downSample            raytracer.cpp:459
+//   EyeRayGenerator::init / generate      raytracer.cpp:292 / 319   (row-sample timing only)
+//   RayTracer::rayTrace, Vec3f::toPixel   raytracer.cpp:385, parser.h:88
+//   write_ppm                             ppm.cpp:4
+// The reference's compile-time AA switch (raytracer.cpp:26-28) only acts inside
+// its main(); this shim passes the factor at run time the same way main does
+// (raytracer.cpp:506-517).
+#define main reference_main_not_used
+#include "raytracer.cpp"
+#undef main
+
+#include <atomic>
+#include <cstring>
+
+namespace {
+struct RefHandle {
+    parser::Scene scene;
+    RayTracer *tracer = nullptr;
+    double build_seconds = 0;
+};
+thread_local std::string g_err;
+}  // namespace
+
+extern "C" {
+
+const char *ref_last_error() { return g_err.c_str(); }
+
+void *ref_open(const char *xml_path) {
+    try {
+        auto *h = new RefHandle();
+        h->scene.loadFromXml(xml_path);
+        auto t0 = std::chrono::high_resolution_clock::now();
+        h->tracer = new RayTracer(h->scene);
+        auto t1 = std::chrono::high_resolution_clock::now();
+        h->build_seconds = std::chrono::duration<double>(t1 - t0).count();
+        return h;
+    } catch (std::exception &e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+
+void ref_close(void *hp) {
+    auto *h = (RefHandle *) hp;
+    if (!h) return;
+    delete h->tracer;  // (the reference leaks its BVHNode tree; so do we)
+    delete h;
+}
+
+double ref_build_seconds(void *hp) { return ((RefHandle *) hp)->build_seconds; }
+
+// counts[0..6] = vertices, triangles(<Triangle>), meshes, mesh faces, spheres, materials, lights; [7]=cameras
+void ref_counts(void *hp, int *counts) {
+    auto &s = ((RefHandle *) hp)->scene;
+    int faces = 0;
+    for (auto &m: s.meshes) faces += (int) m.faces.size();
+    counts[0] = (int) s.vertex_data.size();
+    counts[1] = (int) s.triangles.size();
+    counts[2] = (int) s.meshes.size();
+    counts[3] = faces;
+    counts[4] = (int) s.spheres.size();
+    counts[5] = (int) s.materials.size();
+    counts[6] = (int) s.point_lights.size();
+    counts[7] = (int) s.cameras.size();
+}
+
+// Flat copies of what the reference's own loader parsed (used to check the product's XML
+// reader against tinyxml2 + parser.cpp).  Layouts match include/rt_b200.h.
+void ref_copy_vertices(void *hp, float *out) {
+    auto &s = ((RefHandle *) hp)->scene;
+    for (size_t i = 0; i < s.vertex_data.size(); i++) {
+        out[3 * i] = s.vertex_data[i].x;
+        out[3 * i + 1] = s.vertex_data[i].y;
+        out[3 * i + 2] = s.vertex_data[i].z;
+    }
+}
+
+// triangle list in the order of raytracer.cpp:336-341: {v0,v1,v2,material} per triangle
+void ref_copy_triangles(void *hp, int *out) {
+    auto &s = ((RefHandle *) hp)->scene;
+    size_t k = 0;
+    for (auto &t: s.triangles) {
+        out[k++] = t.indices.v0_id;
+        out[k++] = t.indices.v1_id;
+        out[k++] = t.indices.v2_id;
+        out[k++] = t.material_id;
+    }
+    for (auto &m: s.meshes)
+        for (auto &f: m.faces) {
+            out[k++] = f.v0_id;
+            out[k++] = f.v1_id;
+            out[k++] = f.v2_id;
+            out[k++] = m.material_id;
+        }
+}
+
+// {material_id, center_vertex_id} ints and radius floats
+void ref_copy_spheres(void *hp, int *ids, float *radius) {
+    auto &s = ((RefHandle *) hp)->scene;
+    for (size_t i = 0; i < s.spheres.size(); i++) {
+        ids[2 * i] = s.spheres[i].material_id;
+        ids[2 * i + 1] = s.spheres[i].center_vertex_id;
+        radius[i] = s.spheres[i].radius;
+    }
+}
+
+// 13 floats + is_mirror per material: ambient, diffuse, specular, mirror, phong
+void ref_copy_materials(void *hp, float *out13, int *is_mirror) {
+    auto &s = ((RefHandle *) hp)->scene;
+    for (size_t i = 0; i < s.materials.size(); i++) {
+        auto &m = s.materials[i];
+        float *o = out13 + 13 * i;
+        o[0] = m.ambient.x, o[1] = m.ambient.y, o[2] = m.ambient.z;
+        o[3] = m.diffuse.x, o[4] = m.diffuse.y, o[5] = m.diffuse.z;
+        o[6] = m.specular.x, o[7] = m.specular.y, o[8] = m.specular.z;
+        o[9] = m.mirror.x, o[10] = m.mirror.y, o[11] = m.mirror.z;
+        o[12] = m.phong_exponent;
+        is_mirror[i] = m.is_mirror ? 1 : 0;
+    }
+}
+
+void ref_copy_lights(void *hp, float *out6) {
+    auto &s = ((RefHandle *) hp)->scene;
+    for (size_t i = 0; i < s.point_lights.size(); i++) {
+        auto &l = s.point_lights[i];
+        float *o = out6 + 6 * i;
+        o[0] = l.position.x, o[1] = l.position.y, o[2] = l.position.z;
+        o[3] = l.intensity.x, o[4] = l.intensity.y, o[5] = l.intensity.z;
+    }
+}
+
+// globals: ambient(3 floats), eps; ints: background(3), max depth
+void ref_copy_globals(void *hp, float *f4, int *i4) {
+    auto &s = ((RefHandle *) hp)->scene;
+    f4[0] = s.ambient_light.x, f4[1] = s.ambient_light.y, f4[2] = s.ambient_light.z;
+    f4[3] = s.shadow_ray_epsilon;
+    i4[0] = s.background_color.x, i4[1] = s.background_color.y, i4[2] = s.background_color.z;
+    i4[3] = s.max_recursion_depth;
+}
+
+// camera i: 14 floats (pos, gaze, up, l r b t, dist), 2 ints (w,h), name
+void ref_copy_camera(void *hp, int i, float *f14, int *wh, char *name, int name_cap) {
+    auto &c = ((RefHandle *) hp)->scene.cameras[i];
+    f14[0] = c.position.x, f14[1] = c.position.y, f14[2] = c.position.z;
+    f14[3] = c.gaze.x, f14[4] = c.gaze.y, f14[5] = c.gaze.z;
+    f14[6] = c.up.x, f14[7] = c.up.y, f14[8] = c.up.z;
+    f14[9] = c.near_plane.x, f14[10] = c.near_plane.y, f14[11] = c.near_plane.z, f14[12] = c.near_plane.w;
+    f14[13] = c.near_distance;
+    wh[0] = c.image_width, wh[1] = c.image_height;
+    snprintf(name, name_cap, "%s", c.image_name.c_str());
+}
+
+// reference BVH statistics (bvh.h:81-105 flattened tree): nodes, leaves, max leaf size, max depth
+void ref_bvh_stats(void *hp, int *out4) {
+    auto &nodes = ((RefHandle *) hp)->tracer->tree.nodes;
+    int leaves = 0, maxleaf = 0, maxdepth = 0;
+    for (auto &n: nodes) {
+        if (n.isLeaf()) {
+            leaves++;
+            maxleaf = std::max(maxleaf, (int) (n.triangles.size() + n.spheres.size()));
+        }
+        maxdepth = std::max(maxdepth, n.depth);
+    }
+    out4[0] = (int) nodes.size(), out4[1] = leaves, out4[2] = maxleaf, out4[3] = maxdepth;
+}
+
+// The render step of the reference's main loop (raytracer.cpp:505-517) for camera `cam_idx` with
+// a run-time AA factor; out_w/out_h > 0 override <ImageResolution> (the "8K" config).  Writes
+// out_w*out_h*3 bytes.  Returns the seconds spent inside RayTracer::render (render-only) or < 0.
+// Note raytracer.cpp:363 multiplies width*height in int: sub-sample images of 2^31 pixels or more
+// cannot be rendered by the reference (use ref_time_rows for those).
+double ref_render(void *hp, int cam_idx, int aa, int out_w, int out_h, unsigned char *out) {
+    auto *h = (RefHandle *) hp;
+    try {
+        Camera camera = h->scene.cameras[cam_idx];
+        if (out_w > 0) camera.image_width = out_w;
+        if (out_h > 0) camera.image_height = out_h;
+        long long sub = (long long) camera.image_width * aa * (long long) camera.image_height * aa;
+        if (sub >= (1LL << 31) / 1) {
+            g_err = "sub-sample image too large for the reference's int arithmetic (raytracer.cpp:363)";
+            return -1;
+        }
+        camera.image_width *= aa;
+        camera.image_height *= aa;
+        auto t0 = std::chrono::high_resolution_clock::now();
+        auto image = h->tracer->render(camera);
+        auto t1 = std::chrono::high_resolution_clock::now();
+        if (aa > 1) {
+            auto small = ImageProcessor::downSample(image, camera.image_width, camera.image_height, aa);
+            delete[] image;
+            image = small;
+            camera.image_width /= aa;
+            camera.image_height /= aa;
+        }
+        memcpy(out, image, (size_t) camera.image_width * camera.image_height * 3);
+        delete[] image;
+        return std::chrono::duration<double>(t1 - t0).count();
+    } catch (std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+// Bounded sample of a (possibly > 2^31 pixel) sub-sample image for CPU timing: traces sub-sample
+// rows row0, row0+row_stride, ... (n_rows of them) of the (out_w*aa) x (out_h*aa) grid with the
+// reference's own generate / rayTrace / toPixel, rows dealt round-robin to `threads` std::threads
+// exactly like raytracer.cpp:352-360 deals rows.  If rows_out != NULL it receives the quantised
+// sub-samples (n_rows * out_w*aa * 3 bytes).  Returns seconds.
+double ref_time_rows(void *hp, int cam_idx, int aa, int out_w, int out_h, long long row0, long long row_stride,
+                     int n_rows, int threads, unsigned char *rows_out) {
+    auto *h = (RefHandle *) hp;
+    Camera camera = h->scene.cameras[cam_idx];
+    if (out_w > 0) camera.image_width = out_w;
+    if (out_h > 0) camera.image_height = out_h;
+    camera.image_width *= aa;
+    camera.image_height *= aa;
+    auto *rt = h->tracer;
+    rt->currentCamera = &camera;
+    rt->eyeRayGenerator.init(&camera);
+    if (threads <= 0) {
+        threads = (int) std::thread::hardware_concurrency();
+        if (threads == 0) threads = 8;
+    }
+    const int width = camera.image_width;
+    auto t0 = std::chrono::high_resolution_clock::now();
+    std::vector<std::thread> pool;
+    for (int ti = 0; ti < threads; ti++) {
+        pool.emplace_back([=]() {
+            Pixel px;
+            for (int k = ti; k < n_rows; k += threads) {
+                int row = (int) (row0 + row_stride * k);
+                for (int col = 0; col < width; col++) {
+                    Ray eyeRay = rt->eyeRayGenerator.generate(row, col);
+                    auto c = rt->rayTrace(eyeRay);
+                    c.toPixel(px);
+                    if (rows_out) memcpy(rows_out + ((size_t) k * width + col) * 3, px, 3);
+                }
+            }
+        });
+    }
+    for (auto &t: pool) t.join();
+    auto t1 = std::chrono::high_resolution_clock::now();
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+int ref_hardware_threads() {
+    int n = (int) std::thread::hardware_concurrency();
+    return n ? n : 8;
+}
+
+// ppm.cpp:4 (throws on failure)
+int ref_write_ppm(const char *path, unsigned char *rgb, int w, int h) {
+    try {
+        write_ppm(path, rgb, w, h);
+        return 0;
+    } catch (std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+}  // extern "C"
