@@ -194,6 +194,9 @@ int rt_render_multi(RtScene *const *scenes, int n_gpus, const RtCamera *cam, int
 const char *rt_last_error(void);
 int rt_abi_version(void);
 int rt_device_count(void);
+/* cudaSetDevice for callers that do not link the CUDA runtime themselves (rt_scene_create builds on
+ * the CURRENT device). */
+int rt_set_device(int device);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,209 @@
+// bvh_host.cpp — host binned-SAH BVH2 builder (quality yardstick / RT_BUILD_SAH_HOST), the
+// outward box padding and the SAH cost metric shared with the GPU builder.
+//
+// The traversal BVH replaces the reference's acceleration structure (bvh.h:37-181).  It only has
+// to be conservative: a node box must contain everything the exact primitive tests can report as
+// a hit, so the hit SET equals the reference's and ties are settled by ref_order.cpp's ranks.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+
+#include "rt_internal.h"
+
+namespace rtb {
+
+namespace {
+
+inline void grow(Aabb &a, const Aabb &b) {
+    for (int k = 0; k < 3; k++) {
+        a.mn[k] = std::min(a.mn[k], b.mn[k]);
+        a.mx[k] = std::max(a.mx[k], b.mx[k]);
+    }
+}
+inline Aabb empty_box() { return Aabb{{FLT_MAX, FLT_MAX, FLT_MAX}, {-FLT_MAX, -FLT_MAX, -FLT_MAX}}; }
+inline float half_area(const Aabb &b) {
+    float dx = b.mx[0] - b.mn[0], dy = b.mx[1] - b.mn[1], dz = b.mx[2] - b.mn[2];
+    if (dx < 0 || dy < 0 || dz < 0) return 0;
+    return dx * dy + dy * dz + dz * dx;
+}
+
+constexpr int kBins = 32;
+constexpr float kCostNode = 1.0f;  // one two-box node step
+constexpr float kCostPrim = 1.6f;  // one exact (division-bearing) primitive test
+
+struct SahBuilder {
+    const std::vector<Aabb> &bounds;
+    std::vector<int> ids;
+    HostBvh &out;
+
+    SahBuilder(const std::vector<Aabb> &b, HostBvh &o) : bounds(b), out(o) {}
+
+    int encode_leaf(int lo, int hi) { return ~((lo << 3) | (hi - lo - 1)); }
+
+    // returns the child reference for ids[lo,hi) and writes its box
+    int build(int lo, int hi, int depth, Aabb &box) {
+        box = empty_box();
+        Aabb cbox = empty_box();
+        for (int i = lo; i < hi; i++) {
+            const Aabb &b = bounds[ids[i]];
+            grow(box, b);
+            for (int k = 0; k < 3; k++) {
+                float c = 0.5f * (b.mn[k] + b.mx[k]);
+                cbox.mn[k] = std::min(cbox.mn[k], c);
+                cbox.mx[k] = std::max(cbox.mx[k], c);
+            }
+        }
+        const int n = hi - lo;
+        if (depth > out.max_depth) out.max_depth = depth;
+        if (n == 1) return encode_leaf(lo, hi);
+
+        int best_axis = -1, best_bin = -1;
+        float best_cost = FLT_MAX;
+        const float parent_area = half_area(box);
+        for (int axis = 0; axis < 3; axis++) {
+            const float c0 = cbox.mn[axis], c1 = cbox.mx[axis];
+            if (!(c1 > c0)) continue;
+            const float scale = kBins / (c1 - c0);
+            Aabb bb[kBins];
+            int cnt[kBins];
+            for (int b = 0; b < kBins; b++) bb[b] = empty_box(), cnt[b] = 0;
+            for (int i = lo; i < hi; i++) {
+                const Aabb &pb = bounds[ids[i]];
+                int b = std::min(kBins - 1, std::max(0, (int) ((0.5f * (pb.mn[axis] + pb.mx[axis]) - c0) * scale)));
+                cnt[b]++;
+                grow(bb[b], pb);
+            }
+            float right_area[kBins];
+            Aabb acc = empty_box();
+            for (int b = kBins - 1; b > 0; b--) {
+                grow(acc, bb[b]);
+                right_area[b] = half_area(acc);
+            }
+            acc = empty_box();
+            int nl = 0;
+            for (int b = 0; b < kBins - 1; b++) {
+                grow(acc, bb[b]);
+                nl += cnt[b];
+                if (nl == 0 || nl == n) continue;
+                float cost = half_area(acc) * nl + right_area[b + 1] * (n - nl);
+                if (cost < best_cost) best_cost = cost, best_axis = axis, best_bin = b;
+            }
+        }
+        const float leaf_cost = kCostPrim * n;
+        const float split_cost = best_axis < 0 ? FLT_MAX
+                                 : kCostNode + kCostPrim * best_cost / (parent_area > 0 ? parent_area : 1e-30f);
+        if (n <= kMaxLeafPrims && (best_axis < 0 || leaf_cost <= split_cost)) return encode_leaf(lo, hi);
+
+        int mid;
+        if (best_axis >= 0) {
+            const float c0 = cbox.mn[best_axis], scale = kBins / (cbox.mx[best_axis] - c0);
+            auto it = std::partition(ids.begin() + lo, ids.begin() + hi, [&](int id) {
+                const Aabb &pb = bounds[id];
+                int b = std::min(kBins - 1, std::max(0, (int) ((0.5f * (pb.mn[best_axis] + pb.mx[best_axis]) - c0) * scale)));
+                return b <= best_bin;
+            });
+            mid = (int) (it - ids.begin());
+        } else {
+            mid = lo + n / 2;  // all centroids coincide: split the list
+        }
+        if (mid == lo || mid == hi) mid = lo + n / 2;
+
+        const int me = (int) out.nodes.size();
+        out.nodes.push_back(HostNode());
+        Aabb b0, b1;
+        int c0 = build(lo, mid, depth + 1, b0);
+        int c1 = build(mid, hi, depth + 1, b1);
+        HostNode &nd = out.nodes[me];
+        for (int k = 0; k < 3; k++) {
+            nd.c0mn[k] = b0.mn[k], nd.c0mx[k] = b0.mx[k];
+            nd.c1mn[k] = b1.mn[k], nd.c1mx[k] = b1.mx[k];
+        }
+        nd.child0 = c0;
+        nd.child1 = c1;
+        return me;
+    }
+};
+
+}  // namespace
+
+void build_bvh_sah_host(const std::vector<Aabb> &bounds, HostBvh &out) {
+    out = HostBvh();
+    const int np = (int) bounds.size();
+    if (np == 0) return;
+    SahBuilder b(bounds, out);
+    b.ids.resize(np);
+    for (int i = 0; i < np; i++) b.ids[i] = i;
+    Aabb box;
+    out.nodes.reserve((size_t) np);
+    int root = b.build(0, np, 0, box);
+    if (root < 0) {  // the whole scene is one leaf: give it a parent so that node 0 always exists
+        HostNode nd;
+        for (int k = 0; k < 3; k++) {
+            nd.c0mn[k] = box.mn[k], nd.c0mx[k] = box.mx[k];
+            nd.c1mn[k] = FLT_MAX, nd.c1mx[k] = -FLT_MAX;
+        }
+        nd.child0 = root;
+        nd.child1 = kEmptyChild;
+        out.nodes.push_back(nd);
+    }
+    out.prim_order = b.ids;
+    out.sah_cost = bvh_sah_cost(out);
+}
+
+// Padding: per axis  1e-4 * extent  +  4e-6 * (scene diagonal + largest |coordinate| of the box).
+// The first term follows the box, the second keeps flat (zero-thickness) boxes and boxes far from
+// the world origin a few dozen ulps thick, so that the fp32 slab test with FMA cannot reject a ray
+// the exact primitive test accepts.
+void pad_boxes(HostBvh &bvh, const std::vector<Aabb> &bounds) {
+    Aabb scene = empty_box();
+    for (auto &b: bounds) grow(scene, b);
+    float diag = 0;
+    if (!bounds.empty()) {
+        double s = 0;
+        for (int k = 0; k < 3; k++) s += (double) (scene.mx[k] - scene.mn[k]) * (scene.mx[k] - scene.mn[k]);
+        diag = (float) std::sqrt(s);
+    }
+    auto pad = [&](float *mn, float *mx) {
+        if (mn[0] > mx[0]) return;  // empty child
+        for (int k = 0; k < 3; k++) {
+            float ext = mx[k] - mn[k];
+            float mag = std::max(std::fabs(mn[k]), std::fabs(mx[k]));
+            float p = 1e-4f * ext + 4e-6f * (diag + mag);
+            mn[k] -= p;
+            mx[k] += p;
+        }
+    };
+    for (auto &n: bvh.nodes) {
+        pad(n.c0mn, n.c0mx);
+        pad(n.c1mn, n.c1mx);
+    }
+}
+
+float bvh_sah_cost(const HostBvh &bvh) {
+    if (bvh.nodes.empty()) return 0;
+    // root box = union of the root's children
+    const HostNode &r = bvh.nodes[0];
+    Aabb root = empty_box();
+    Aabb a, b;
+    for (int k = 0; k < 3; k++) a.mn[k] = r.c0mn[k], a.mx[k] = r.c0mx[k], b.mn[k] = r.c1mn[k], b.mx[k] = r.c1mx[k];
+    grow(root, a);
+    if (r.child1 != kEmptyChild) grow(root, b);
+    const float ra = half_area(root);
+    if (!(ra > 0)) return 0;
+    double cost = kCostNode;  // the root step
+    for (auto &n: bvh.nodes) {
+        const float *mns[2] = {n.c0mn, n.c1mn}, *mxs[2] = {n.c0mx, n.c1mx};
+        const int ch[2] = {n.child0, n.child1};
+        for (int c = 0; c < 2; c++) {
+            if (ch[c] == kEmptyChild) continue;
+            Aabb cb;
+            for (int k = 0; k < 3; k++) cb.mn[k] = mns[c][k], cb.mx[k] = mxs[c][k];
+            float p = half_area(cb) / ra;
+            if (ch[c] >= 0) cost += kCostNode * p;
+            else cost += kCostPrim * p * (((~ch[c]) & 7) + 1);
+        }
+    }
+    return (float) cost;
+}
+
+}  // namespace rtb

@@ -1,0 +1,45 @@
+// ppm_writer.cpp — ASCII P3 writer, byte-identical to the reference's ppm.cpp:4-39, but table-driven:
+// the reference spends ~0.25 s of horse_and_mug's 0.5 s in one fprintf per channel;
+// here each row is formatted into a buffer with a 256-entry decimal table and written once.
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <vector>
+
+#include "scene.h"
+
+namespace {
+struct DecTable {
+    char txt[256][4];  // "0 ".."255 " without terminator
+    unsigned char len[256];
+    DecTable() {
+        for (int v = 0; v < 256; v++) {
+            char tmp[8];
+            int n = snprintf(tmp, sizeof tmp, "%d ", v);
+            memcpy(txt[v], tmp, (size_t) n);
+            len[v] = (unsigned char) n;
+        }
+    }
+};
+}  // namespace
+
+void write_ppm(const char *filename, unsigned char *data, int width, int height) {
+    static const DecTable T;
+    FILE *out = fopen(filename, "w");
+    if (!out) throw std::runtime_error("Error: The ppm file cannot be opened for writing.");
+    fprintf(out, "P3\n%d %d\n255\n", width, height);
+    std::vector<char> row((size_t) (width > 0 ? width : 0) * 12 + 2);
+    for (int j = 0; j < height; j++) {
+        const unsigned char *src = data + (size_t) j * (size_t) width * 3;
+        char *w = row.data();
+        for (size_t k = 0, n = (size_t) width * 3; k < n; k++) {
+            unsigned v = src[k];
+            memcpy(w, T.txt[v], 4);
+            w += T.len[v];
+        }
+        if (width > 0) w--;  // the last value of a row carries no trailing space (ppm.cpp:24-27)
+        *w++ = '\n';
+        fwrite(row.data(), 1, (size_t) (w - row.data()), out);
+    }
+    fclose(out);
+}

@@ -1,0 +1,78 @@
+// rt_internal.h — structures shared by the host-side builders and the CUDA kernels.
+#pragma once
+
+#include <cstdint>
+#include <vector>
+
+#include "rt_b200.h"
+
+namespace rtb {
+
+// ---------------------------------------------------------------------------------------------
+// Device data layout (everything is read-only during rendering and, at < 5 MB for the largest
+// shipped scene, L2-resident; all records are 16-byte aligned so every fetch is one LDG.128).
+//
+//  nodes      float4[4 * n_nodes]   BVH2, both children's boxes in the parent (64 B per node):
+//                                    [0] = c0.min.x c0.max.x c0.min.y c0.max.y
+//                                    [1] = c1.min.x c1.max.x c1.min.y c1.max.y
+//                                    [2] = c0.min.z c0.max.z c1.min.z c1.max.z
+//                                    [3] = bits(child0) bits(child1) - -
+//                                   child >= 0: inner node index; child < 0: leaf, ~child = (first << 3) | (count - 1)
+//                                   into `prims`; kEmptyChild: no child (box inverted, never hit)
+//  prims      float4[3 * n_prims]   primitives in leaf order (48 B each):
+//                                    triangle [0] = a.x a.y a.z bits(prim_id)      (a = vertex v0)
+//                                             [1] = (a-b).xyz  bits(0)
+//                                             [2] = (a-c).xyz  (a-b).y*(a-c).z - (a-c).y*(a-b).z   (ray-independent minor)
+//                                    sphere   [0] = c.x c.y c.z bits(prim_id)
+//                                             [1] = radius 0 0 bits(1)
+//                                   prim_id: triangles 0..nt-1 in the reference's list order, spheres nt..nt+ns-1
+//  tri_nm     float4[nt]            unit geometric normal (raytracer.cpp:346) + bits(material_id)
+//  sph_cr     float4[ns]            centre + radius; sph_mat int[ns]
+//  ranks      uint32[8 * n_prims]   visit rank of prim_id in the reference's traversal order for each
+//                                   ray-direction sign octant (bit a <=> dir[a] > 0) — exact-t tie breaking
+//  materials  float4[4 * nm]        [0] = ka.xyz phong  [1] = kd.xyz bits(is_mirror)  [2] = ks.xyz 0  [3] = km.xyz 0
+//  lights     float4[2 * nl]        [0] = position.xyz  [1] = intensity.xyz
+// ---------------------------------------------------------------------------------------------
+
+constexpr int kEmptyChild = 0x7fffffff;
+constexpr int kMaxLeafPrims = 8;
+constexpr int kMaxSupportedDepth = 32;  // max_recursion_depth accepted by rt_scene_create
+
+struct Aabb {
+    float mn[3], mx[3];
+};
+
+struct HostNode {  // one 64-byte device node, host view
+    float c0mn[3], c0mx[3], c1mn[3], c1mx[3];
+    int child0, child1;
+};
+
+struct HostBvh {
+    std::vector<HostNode> nodes;      // node 0 is the root (absent when there are no primitives)
+    std::vector<int> prim_order;      // leaf-ordered prim ids
+    int max_depth = 0;
+    float sah_cost = 0;
+};
+
+// Bounds of every primitive exactly as the reference computes them (parser.h:272-317): vertex
+// min/max for triangles, centre -/+ radius (float ops) for spheres.
+void primitive_bounds(const RtSceneDesc &d, std::vector<Aabb> &out);
+
+// Reference-order ranks: rebuilds the reference's midpoint-split tree
+// (bvh.h:48-163) with the same float operations and writes, for each of the 8 direction-sign
+// octants, the position of every primitive in the reference's leaf visit order.
+struct RefTreeStats {
+    int nodes = 0, leaves = 0, max_leaf = 0, max_depth = 0;
+};
+void build_reference_ranks(const RtSceneDesc &d, std::vector<uint32_t> &ranks /* [8][np] */, RefTreeStats &stats);
+
+// Host binned-SAH BVH2 (quality yardstick and fallback for tiny scenes).
+void build_bvh_sah_host(const std::vector<Aabb> &bounds, HostBvh &out);
+
+// Outward padding applied to every child box before upload (conservative node test; the
+// primitive tests stay exact).  See DESIGN.md "why the boxes are padded".
+void pad_boxes(HostBvh &bvh, const std::vector<Aabb> &bounds);
+
+float bvh_sah_cost(const HostBvh &bvh);
+
+}  // namespace rtb

@@ -1,79 +1,25 @@
-"""ctypes plumbing shared by the tests, bench.py and __graft_entry__.py.
+"""Test/bench plumbing: binds the CHECKERS (oracle, reference) and the golden fixtures.
 
-Three libraries are bound here:
-  * the PRODUCT  : raytracer-ceng477-graphics-hw-1_b200/libwhitted_b200.so (CUDA, C-ABI of include/rt_b200.h)
-                   and .../libwhitted_host.so (XML scene reader + PPM writer, host only)
+  * the PRODUCT lives in raytracer-ceng477-graphics-hw-1_b200/rt_b200.py (re-exported here)
   * the ORACLE   : oracle/liboracle.so (plain-C restatement; checker only)
   * the REFERENCE: oracle/_ref/libref.so (unmodified reference behind oracle/ref_shim.cpp; checker /
                    CPU baseline only; built in the authoring container, shipped to the GPU box)
 """
 import ctypes as C
 import os
+import sys
 
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "raytracer-ceng477-graphics-hw-1_b200")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+if PKG not in sys.path:
+    sys.path.insert(0, PKG)
 
-
-class RtVec3(C.Structure):
-    _fields_ = [("x", C.c_float), ("y", C.c_float), ("z", C.c_float)]
-
-
-class RtMaterial(C.Structure):
-    _fields_ = [("ambient", RtVec3), ("diffuse", RtVec3), ("specular", RtVec3), ("mirror", RtVec3),
-                ("phong_exponent", C.c_float), ("is_mirror", C.c_int32)]
-
-
-class RtPointLight(C.Structure):
-    _fields_ = [("position", RtVec3), ("intensity", RtVec3)]
-
-
-class RtTriangle(C.Structure):
-    _fields_ = [("v0_id", C.c_int32), ("v1_id", C.c_int32), ("v2_id", C.c_int32), ("material_id", C.c_int32)]
-
-
-class RtSphere(C.Structure):
-    _fields_ = [("material_id", C.c_int32), ("center_vertex_id", C.c_int32), ("radius", C.c_float)]
-
-
-class RtSceneDesc(C.Structure):
-    _fields_ = [("vertices", C.c_void_p), ("n_vertices", C.c_int32),
-                ("triangles", C.c_void_p), ("n_triangles", C.c_int32),
-                ("spheres", C.c_void_p), ("n_spheres", C.c_int32),
-                ("materials", C.c_void_p), ("n_materials", C.c_int32),
-                ("lights", C.c_void_p), ("n_lights", C.c_int32),
-                ("ambient_light", RtVec3), ("background", C.c_int32 * 3),
-                ("shadow_ray_epsilon", C.c_float), ("max_recursion_depth", C.c_int32)]
-
-
-class RtCamera(C.Structure):
-    _fields_ = [("position", RtVec3), ("gaze", RtVec3), ("up", RtVec3),
-                ("l", C.c_float), ("r", C.c_float), ("b", C.c_float), ("t", C.c_float),
-                ("near_distance", C.c_float), ("image_width", C.c_int32), ("image_height", C.c_int32)]
-
-
-class RtBuildOptions(C.Structure):
-    _fields_ = [("builder", C.c_int32), ("brute_force", C.c_int32), ("reserved", C.c_int32 * 6)]
-
-
-class RtStats(C.Structure):
-    _fields_ = [("primary_rays", C.c_uint64), ("reflection_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
-                ("shadow_occluded", C.c_uint64), ("ms_render", C.c_float), ("ms_d2h", C.c_float),
-                ("ms_total", C.c_float), ("n_launches", C.c_int32), ("reserved", C.c_int32 * 3)]
-
-    @property
-    def total_rays(self):
-        return self.primary_rays + self.reflection_rays + self.shadow_rays
-
-
-class RtSceneInfo(C.Structure):
-    _fields_ = [("n_triangles", C.c_int32), ("n_spheres", C.c_int32), ("bvh_nodes", C.c_int32),
-                ("bvh_max_depth", C.c_int32), ("ref_tree_nodes", C.c_int32), ("ref_tree_leaves", C.c_int32),
-                ("ref_tree_max_leaf", C.c_int32), ("ref_tree_max_depth", C.c_int32),
-                ("ms_build_host", C.c_float), ("ms_build_device", C.c_float), ("bvh_sah_cost", C.c_float),
-                ("builder", C.c_int32), ("device", C.c_int32), ("reserved", C.c_int32 * 3)]
+import rt_b200  # noqa: E402
+from rt_b200 import (RayTracer, RtBuildOptions, RtCamera, RtMaterial, RtPointLight, RtSceneDesc, RtSceneInfo,  # noqa: E402,F401
+                     RtSphere, RtStats, RtTriangle, RtVec3, Scene, host_lib, load_scene_xml, write_ppm)
 
 
 class OrStats(C.Structure):
@@ -84,70 +30,6 @@ class OrStats(C.Structure):
     @property
     def total_rays(self):
         return self.primary_rays + self.reflection_rays + self.shadow_rays
-
-
-class Scene:
-    """Flat scene arrays (numpy) + the RtSceneDesc pointing at them + cameras."""
-
-    def __init__(self, vertices, triangles, sphere_ids, sphere_radius, materials13, is_mirror, lights6,
-                 ambient, eps, background, max_depth, cameras):
-        self.vertices = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
-        self.triangles = np.ascontiguousarray(triangles, dtype=np.int32).reshape(-1, 4)
-        ns = len(sphere_radius)
-        self.spheres = np.zeros(ns, dtype=np.dtype([("material_id", "<i4"), ("center_vertex_id", "<i4"), ("radius", "<f4")]))
-        if ns:
-            ids = np.asarray(sphere_ids, dtype=np.int32).reshape(-1, 2)
-            self.spheres["material_id"] = ids[:, 0]
-            self.spheres["center_vertex_id"] = ids[:, 1]
-            self.spheres["radius"] = np.asarray(sphere_radius, dtype=np.float32)
-        m13 = np.asarray(materials13, dtype=np.float32).reshape(-1, 13)
-        self.materials = np.zeros(len(m13), dtype=np.dtype([("f", "<f4", 13), ("is_mirror", "<i4")]))
-        self.materials["f"] = m13
-        self.materials["is_mirror"] = np.asarray(is_mirror, dtype=np.int32)
-        self.lights = np.ascontiguousarray(lights6, dtype=np.float32).reshape(-1, 6)
-        self.cameras = cameras  # list of (RtCamera, name)
-        d = RtSceneDesc()
-        d.vertices = self.vertices.ctypes.data
-        d.n_vertices = len(self.vertices)
-        d.triangles = self.triangles.ctypes.data
-        d.n_triangles = len(self.triangles)
-        d.spheres = self.spheres.ctypes.data
-        d.n_spheres = ns
-        d.materials = self.materials.ctypes.data
-        d.n_materials = len(self.materials)
-        d.lights = self.lights.ctypes.data
-        d.n_lights = len(self.lights)
-        d.ambient_light = RtVec3(*[float(a) for a in ambient])
-        d.background = (C.c_int32 * 3)(*[int(b) for b in background])
-        d.shadow_ray_epsilon = float(eps)
-        d.max_recursion_depth = int(max_depth)
-        self.desc = d
-
-    def camera(self, name_or_index=0, width=None, height=None):
-        if isinstance(name_or_index, int):
-            cam, name = self.cameras[name_or_index]
-        else:
-            cam, name = next((c, n) for c, n in self.cameras if n == name_or_index or n == name_or_index + ".ppm")
-        out = RtCamera.from_buffer_copy(cam)
-        if width:
-            out.image_width = width
-        if height:
-            out.image_height = height
-        return out
-
-    def digest(self):
-        """sha256 over every parsed value (loader parity)."""
-        import hashlib
-        h = hashlib.sha256()
-        for a in (self.vertices, self.triangles, self.spheres, self.materials, self.lights):
-            h.update(a.tobytes())
-        d = self.desc
-        h.update(np.array([d.ambient_light.x, d.ambient_light.y, d.ambient_light.z, d.shadow_ray_epsilon], dtype=np.float32).tobytes())
-        h.update(np.array(list(d.background) + [d.max_recursion_depth], dtype=np.int32).tobytes())
-        for cam, name in self.cameras:
-            h.update(bytes(cam))
-            h.update(name.encode())
-        return h.hexdigest()
 
 
 # ----------------------------------------------------------------------------- reference (libref.so)
@@ -328,3 +210,51 @@ def diff_report(a, b):
 def within_tolerance(rep):
     """north_star: |delta| <= 1 per channel on >= 99.9 % of pixels, zero pixels off by more than 8."""
     return rep["gt8"] == 0 and rep["le1"] >= 0.999 * rep["pixels"]
+
+
+# ----------------------------------------------------------------------------- golden fixtures
+
+_manifest = None
+_scene_dir = None
+
+
+def manifest():
+    global _manifest
+    if _manifest is None:
+        import json
+        with open(os.path.join(GOLDEN, "manifest.json")) as f:
+            _manifest = json.load(f)
+    return _manifest
+
+
+def golden_scene_path(name):
+    """Decompresses tests/golden/scenes/<name>.xml.xz into a per-process temp dir, returns the .xml path."""
+    global _scene_dir
+    import lzma
+    import tempfile
+    if _scene_dir is None:
+        _scene_dir = tempfile.mkdtemp(prefix="rtb200_scenes_")
+    out = os.path.join(_scene_dir, name + ".xml")
+    if not os.path.exists(out):
+        with lzma.open(os.path.join(GOLDEN, "scenes", name + ".xml.xz")) as f, open(out + ".tmp", "wb") as g:
+            g.write(f.read())
+        os.replace(out + ".tmp", out)
+    return out
+
+
+_scene_cache = {}
+
+
+def golden_scene(name):
+    if name not in _scene_cache:
+        _scene_cache[name] = load_scene_xml(golden_scene_path(name))
+    return _scene_cache[name]
+
+
+def golden_image(key):
+    import lzma
+    m = manifest()["images"][key]
+    with lzma.open(os.path.join(GOLDEN, "images", key + ".rgb.xz")) as f:
+        raw = f.read()
+    rows = len(m["rows"]) if "rows" in m else m["height"]
+    return np.frombuffer(raw, np.uint8).reshape(rows, m["width"], 3), m

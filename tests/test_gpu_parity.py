@@ -1,0 +1,96 @@
+"""GPU parity: the CUDA path, called through the C-ABI (rt_b200.RayTracer -> rt_render), against the golden
+frames rendered by the unmodified reference, and against the oracle on seeded/ad-hoc inputs.
+
+Tolerance (BASELINE.json north_star): |delta| <= 1 per 8-bit channel on >= 99.9 % of pixels and zero pixels off by
+more than 8.  The design goal is stricter — byte identity — and each test prints the exact counts.
+"""
+import numpy as np
+import pytest
+
+import harness as H
+
+pytestmark = pytest.mark.gpu
+
+ALL_IMAGES = sorted(k for k, v in H.manifest()["images"].items() if "rows" not in v)
+
+_tracers = {}
+
+
+def tracer(scene_name, **kw):
+    key = (scene_name, tuple(sorted(kw.items())))
+    if key not in _tracers:
+        _tracers[key] = H.RayTracer(H.golden_scene(scene_name), **kw)
+    return _tracers[key]
+
+
+@pytest.mark.parametrize("key", ALL_IMAGES)
+def test_golden_frame(key):
+    gold, m = H.golden_image(key)
+    sc = H.golden_scene(m["scene"])
+    cam = sc.camera(m["camera"], m["width"], m["height"])
+    rt = tracer(m["scene"])
+    img = rt.render(cam, m["aa"])
+    rep = H.diff_report(gold, img)
+    st = rt.last_stats
+    print(key, rep, "rays", st.primary_rays, st.reflection_rays, st.shadow_rays, st.shadow_occluded, f"{st.ms_render:.3f} ms")
+    assert H.within_tolerance(rep), rep
+    # Device ray counters against the oracle's known answers.  Primary rays are exact by construction.  The
+    # others are exact whenever every hit decision matches; the one known source of deviation is a ray whose
+    # hit the reference's own un-padded box test culls ("seam holes", SURVEY.md finding 2) while the padded
+    # BVH here reports it — a few sub-samples per million on scenes with zero-thickness boxes.
+    rays = m["rays"]
+    assert st.primary_rays == rays["primary"]
+    for got, want in ((st.reflection_rays, rays["reflection"]), (st.shadow_rays, rays["shadow"]),
+                      (st.shadow_occluded, rays["shadow_occluded"])):
+        assert abs(got - want) <= max(4, 1e-5 * want), (got, want)
+
+
+@pytest.mark.parametrize("key", ["simple.aa1", "cornellbox_front.aa1", "mirror_spheres.aa1", "simple_reflectance.aa1", "monkey.aa1"])
+def test_bvh_equals_brute_force(key):
+    """A conservative BVH must report exactly the hit set of testing every primitive."""
+    _, m = H.golden_image(key)
+    sc = H.golden_scene(m["scene"])
+    cam = sc.camera(m["camera"], 256, 256)
+    a = tracer(m["scene"]).render(cam, 1)
+    b = tracer(m["scene"], brute_force=True).render(cam, 1)
+    assert np.array_equal(a, b)
+
+
+def test_tiles_equal_full_frame():
+    """Interleaved-tile parts (packed and straight-into-frame) reassemble to the single-GPU frame byte for byte."""
+    import torch
+    sc = H.golden_scene("cornellbox")
+    cam = sc.camera(0, 250, 190)  # not a multiple of the tile size
+    rt = tracer("cornellbox")
+    full = rt.render(cam, 2)
+    for world in (2, 3, 8):
+        stride = rt.part_bytes(cam, 0, world)
+        parts = torch.zeros(world * stride, dtype=torch.uint8, device="cuda")
+        frame = torch.zeros(cam.image_height * cam.image_width * 3, dtype=torch.uint8, device="cuda")
+        frame2 = torch.zeros_like(frame)
+        total = 0
+        for r in range(world):
+            st = rt.render_part(cam, 2, r, world, parts.data_ptr() + r * stride)
+            total += st.primary_rays
+            rt.render_part_into_frame(cam, 2, r, world, frame2.data_ptr())
+        rt.assemble(cam, world, parts.data_ptr(), stride, frame.data_ptr())
+        torch.cuda.synchronize()
+        got = frame.cpu().numpy().reshape(full.shape)
+        got2 = frame2.cpu().numpy().reshape(full.shape)
+        assert np.array_equal(got, full), world
+        assert np.array_equal(got2, full), world
+        assert total == cam.image_width * cam.image_height * 4
+
+
+def test_oracle_on_odd_configuration():
+    """Ad-hoc camera/AA the goldens do not cover, against the oracle rendered on the box's CPU."""
+    sc = H.golden_scene("simple_reflectance")
+    cam = sc.camera(0, 97, 61)
+    orc = H.OracleScene(sc)
+    want, ost = orc.render(cam, 7)
+    rt = tracer("simple_reflectance")
+    got = rt.render(cam, 7)
+    rep = H.diff_report(want, got)
+    print(rep)
+    assert H.within_tolerance(rep)
+    assert rt.last_stats.primary_rays == ost.primary_rays
