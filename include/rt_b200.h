@@ -191,6 +191,22 @@ int rt_assemble_tiles(const RtCamera *cam, int part_world, const void *d_parts,
 int rt_render_multi(RtScene *const *scenes, int n_gpus, const RtCamera *cam, int aa_factor,
                     unsigned char *rgb_out, RtStats *stats);
 
+/* ---- host-only hooks: no CUDA call inside, usable on a machine without a GPU.
+ * They expose the host-side logic of rt_scene_create to CPU tests. */
+
+/* The reference-order tie ranks (bvh.h:48-163 rebuilt, raytracer.cpp:190-196
+ * visit order): ranks_out[8][n_triangles + n_spheres]; stats4 = nodes, leaves,
+ * max leaf size, max depth of the reference's tree. Either may be NULL. */
+int rt_host_reference_ranks(const RtSceneDesc *desc, uint32_t *ranks_out, int32_t *stats4);
+/* Builds the host SAH BVH, pads it and checks its invariants (every primitive
+ * in exactly one leaf, every box contains what is below it). Returns the node
+ * count (>= 0) or a negative error. */
+int rt_host_check_bvh(const RtSceneDesc *desc, float *sah_cost, int32_t *max_depth);
+/* The closed forms the kernels use in place of libm's pow and acos
+ * (raytracer.cpp:411-414), compiled for the host. */
+float rt_host_pow_ref(float base, float exponent);
+int rt_host_specular_gate(float cos_theta);
+
 const char *rt_last_error(void);
 int rt_abi_version(void);
 int rt_device_count(void);

@@ -9,6 +9,7 @@
 
 #include <cuda_runtime.h>
 
+#include "exact_math.h"
 #include "render_params.h"
 #include "rt_b200.h"
 #include "rt_internal.h"
@@ -236,6 +237,77 @@ int rt_device_count(void) {
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
     return n;
 }
+
+// ---- host-only hooks (no CUDA call inside): let CPU tests pin host-side logic and closed forms ----
+
+int rt_host_reference_ranks(const RtSceneDesc *desc, uint32_t *ranks_out, int32_t *stats4) {
+    int rc = validate(desc);
+    if (rc != RT_OK) return rc;
+    std::vector<uint32_t> ranks;
+    RefTreeStats st;
+    build_reference_ranks(*desc, ranks, st);
+    if (ranks_out) memcpy(ranks_out, ranks.data(), ranks.size() * sizeof(uint32_t));
+    if (stats4) stats4[0] = st.nodes, stats4[1] = st.leaves, stats4[2] = st.max_leaf, stats4[3] = st.max_depth;
+    return RT_OK;
+}
+
+// builds the host SAH BVH and checks its invariants: every primitive in exactly one leaf, every child box
+// (after padding) contains the bounds of everything below it.  Returns the node count or a negative error.
+int rt_host_check_bvh(const RtSceneDesc *desc, float *sah_cost, int32_t *max_depth) {
+    int rc = validate(desc);
+    if (rc != RT_OK) return rc;
+    std::vector<Aabb> bounds;
+    primitive_bounds(*desc, bounds);
+    HostBvh bvh;
+    build_bvh_sah_host(bounds, bvh);
+    if (sah_cost) *sah_cost = bvh_sah_cost(bvh);
+    if (max_depth) *max_depth = tree_depth(bvh);
+    pad_boxes(bvh, bounds);
+    const int np = (int) bounds.size();
+    std::vector<int> seen((size_t) np, 0);
+    if (np == 0) return bvh.nodes.empty() ? 0 : fail(RT_ERR_STATE, "nodes without primitives");
+    struct Item { int ref; Aabb box; };
+    std::vector<Item> st;
+    auto child_box = [](const HostNode &n, int c) {
+        Aabb b;
+        for (int k = 0; k < 3; k++) b.mn[k] = c ? n.c1mn[k] : n.c0mn[k], b.mx[k] = c ? n.c1mx[k] : n.c0mx[k];
+        return b;
+    };
+    auto inside = [](const Aabb &in, const Aabb &out) {
+        for (int k = 0; k < 3; k++)
+            if (in.mn[k] < out.mn[k] || in.mx[k] > out.mx[k]) return false;
+        return true;
+    };
+    Aabb all = {{-INFINITY, -INFINITY, -INFINITY}, {INFINITY, INFINITY, INFINITY}};
+    st.push_back({0, all});
+    while (!st.empty()) {
+        Item it = st.back();
+        st.pop_back();
+        if (it.ref == kEmptyChild) continue;
+        if (it.ref < 0) {
+            int enc = ~it.ref, first = enc >> 3, count = (enc & 7) + 1;
+            for (int s = first; s < first + count; s++) {
+                if (s >= np) return fail(RT_ERR_STATE, "leaf range out of bounds");
+                int id = bvh.prim_order[s];
+                seen[id]++;
+                if (!inside(bounds[id], it.box)) return fail(RT_ERR_STATE, "primitive outside its leaf box");
+            }
+            continue;
+        }
+        const HostNode &n = bvh.nodes[it.ref];
+        for (int c = 0; c < 2; c++) {
+            int ch = c ? n.child1 : n.child0;
+            if (ch == kEmptyChild) continue;
+            st.push_back({ch, child_box(n, c)});
+        }
+    }
+    for (int i = 0; i < np; i++)
+        if (seen[i] != 1) return fail(RT_ERR_STATE, "primitive not in exactly one leaf");
+    return (int) bvh.nodes.size();
+}
+
+float rt_host_pow_ref(float base, float e) { return pow_ref(base, e); }
+int rt_host_specular_gate(float cos_theta) { return specular_gate(cos_theta) ? 1 : 0; }
 
 int rt_set_device(int device) {
     CU(cudaSetDevice(device));

@@ -15,6 +15,7 @@
 #include <cfloat>
 #include <cstdint>
 
+#include "exact_math.h"
 #include "render_params.h"
 #include "rt_b200.h"
 #include "rt_internal.h"
@@ -43,30 +44,6 @@ RT_DEV V3 xyz(float4 q) { return mk(q.x, q.y, q.z); }
 RT_DEV float std_min(float a, float b) { return (b < a) ? b : a; }
 RT_DEV float std_max(float a, float b) { return (a < b) ? b : a; }
 RT_DEV float clamp_ref(float x, float a, float b) { return std_max(a, std_min(x, b)); }  // parser.h:81-86
-
-// The specular gate `acos(cos)*180/3.1415 <= 90.01` (raytracer.cpp:411-412) is monotone in cos;
-// with glibc's acos it is equivalent to  kGateCos <= cos <= 1  (tests/test_host.py pins this
-// against libm bit by bit around the threshold).
-constexpr unsigned kGateCosBits = 0xB90665D3u;  // -0.000128171683f
-
-// pow((double)base, (double)e) narrowed to float (raytracer.cpp:414).  Integer exponents (every
-// shipped scene: 1, 3, 50, 100) take a square-and-multiply chain in double: a handful of
-// half-ulp double roundings, invisible after the narrowing to float except on a ~1e-7 sliver of
-// inputs; anything else goes through the double-precision pow.
-RT_DEV float pow_ref(float base, float e) {
-    double b = (double) base;
-    if (e >= 0.0f && e <= 1024.0f && e == truncf(e)) {
-        unsigned n = (unsigned) e;
-        double r = 1.0;
-        while (n) {
-            if (n & 1u) r = r * b;
-            b = b * b;
-            n >>= 1;
-        }
-        return (float) r;
-    }
-    return (float) pow(b, (double) e);
-}
 
 struct Ray {
     V3 o, d;
@@ -297,7 +274,7 @@ RT_DEV V3 trace_path(const RenderParams &p, V3 o, V3 d, Counters &cnt) {
             const V3 I = xyz(__ldg(&p.lights[2 * li + 1]));
             const float d2 = dist * dist;
             const V3 E = mk(I.x / d2, I.y / d2, I.z / d2);
-            if (cosTheta >= __uint_as_float(kGateCosBits) && cosTheta <= 1.0f) {
+            if (specular_gate(cosTheta)) {
                 const V3 h = normalize(wi + (-dn));
                 const float c = pow_ref(std_max(0.0f, dot(nn, h)), m0.w);
                 color = color + mulv(xyz(m2) * c, E);

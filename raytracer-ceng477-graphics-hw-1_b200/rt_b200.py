@@ -316,3 +316,53 @@ class RayTracer:
 
     def assemble(self, camera, world, d_parts_ptr, part_stride, d_frame_ptr, stream=0):
         _check(self.L.rt_assemble_tiles(C.byref(camera), world, d_parts_ptr, part_stride, d_frame_ptr, stream))
+
+
+# ----------------------------------------------------------------------------- multi-GPU plumbing (one process per GPU)
+#
+# The frame is cut into RT_TILE x RT_TILE pixel tiles numbered row-major; tile k belongs to rank k % world (the
+# reference deals rows round-robin to its threads the same way, raytracer.cpp:353).  Every rank renders its tiles
+# into a packed buffer [n_my_tiles][RT_TILE][RT_TILE][3]; rank 0 gathers the buffers (one collective per frame,
+# no other data-path communication) and scatters them into the row-major frame.
+
+
+def tile_grid(width, height):
+    return (width + RT_TILE - 1) // RT_TILE, (height + RT_TILE - 1) // RT_TILE
+
+
+def part_tile_ids(width, height, rank, world):
+    tx, ty = tile_grid(width, height)
+    return range(rank, tx * ty, world)
+
+
+def gather_parts(dist, my_tiles, all_parts, rank, dst=0):
+    """One gather of the packed tile buffers to `dst` (torch.distributed; NCCL on GPUs, gloo in the CPU tests).
+    all_parts is a [world, stride] tensor on dst, None elsewhere."""
+    dist.gather(my_tiles, list(all_parts.unbind(0)) if rank == dst else None, dst=dst)
+
+
+def pack_tiles_host(frame, rank, world):
+    """Host restatement of the packed layout rt_render_part writes (tests and debugging only)."""
+    h, w, _ = frame.shape
+    tx, _ = tile_grid(w, h)
+    ids = part_tile_ids(w, h, rank, world)
+    out = np.zeros((len(ids), RT_TILE, RT_TILE, 3), np.uint8)
+    for i, k in enumerate(ids):
+        y0, x0 = (k // tx) * RT_TILE, (k % tx) * RT_TILE
+        blk = frame[y0:y0 + RT_TILE, x0:x0 + RT_TILE]
+        out[i, :blk.shape[0], :blk.shape[1]] = blk
+    return out.reshape(-1)
+
+
+def assemble_tiles_host(parts, width, height, world):
+    """Host restatement of rt_assemble_tiles: parts is [world, stride] uint8."""
+    tx, _ = tile_grid(width, height)
+    frame = np.zeros((height, width, 3), np.uint8)
+    for r in range(world):
+        ids = part_tile_ids(width, height, r, world)
+        tiles = np.asarray(parts[r][:len(ids) * RT_TILE * RT_TILE * 3]).reshape(len(ids), RT_TILE, RT_TILE, 3)
+        for i, k in enumerate(ids):
+            y0, x0 = (k // tx) * RT_TILE, (k % tx) * RT_TILE
+            hh, ww = min(RT_TILE, height - y0), min(RT_TILE, width - x0)
+            frame[y0:y0 + hh, x0:x0 + ww] = tiles[i, :hh, :ww]
+    return frame

@@ -1,0 +1,153 @@
+"""Host-side logic of the product, CPU only: the XML scene reader against the reference loader's parse of every
+shipped scene, loader semantics on hand-written scenes, the P3 writer's byte format, the closed forms that replace
+libm calls, and the host BVH's invariants."""
+import ctypes as C
+import hashlib
+import os
+import struct
+
+import numpy as np
+import pytest
+
+import harness as H
+
+M = H.manifest()
+
+
+@pytest.mark.parametrize("scene", sorted(M["scenes"]))
+def test_xml_loader_matches_reference_loader(scene):
+    """loader_digest was computed from what tinyxml2 + parser.cpp parsed (tests/golden/make_golden.py)."""
+    sc = H.golden_scene(scene)
+    assert sc.digest() == M["scenes"][scene]["loader_digest"]
+    c = M["scenes"][scene]["counts"]
+    assert len(sc.vertices) == c["vertices"]
+    assert len(sc.triangles) == c["triangles"] + c["mesh_faces"]
+    assert len(sc.spheres) == c["spheres"] and len(sc.materials) == c["materials"] and len(sc.lights) == c["lights"]
+    assert [n for _, n in sc.cameras] == M["scenes"][scene]["cameras"]
+
+
+MINI = """<!-- leading comment --><Scene>
+  <MaxRecursionDepth>3</MaxRecursionDepth>
+  <Cameras><Camera id="7"><ImageName>a.ppm</ImageName><ImageResolution>4 2</ImageResolution><NearDistance>1.5</NearDistance>
+    <NearPlane>-1 1 -0.5 0.5</NearPlane><Up>0 1 0</Up><Gaze>0 0 -1</Gaze><Position>1 2 3</Position></Camera></Cameras>
+  <Lights><AmbientLight>25 25 25</AmbientLight><PointLight id="1"><Position>0 0 0</Position><Intensity>1e3 1000 1000</Intensity></PointLight></Lights>
+  <Materials>
+    <Material id="1" type="mirror"><PhongExponent>3</PhongExponent><MirrorReflectance>.5 .5 .5</MirrorReflectance>
+      <AmbientReflectance>1 1 1</AmbientReflectance><DiffuseReflectance>1 0 0</DiffuseReflectance><SpecularReflectance>0 1 0</SpecularReflectance></Material>
+    <Material id="2"><AmbientReflectance>0 0 1</AmbientReflectance><DiffuseReflectance>1 0 0</DiffuseReflectance>
+      <SpecularReflectance>0 1 0</SpecularReflectance><MirrorReflectance>0 0 0</MirrorReflectance><PhongExponent>1</PhongExponent></Material>
+  </Materials>
+  <VertexData>
+     0 0 -2   1 0 -2
+     0 1 -2   5 5 -9</VertexData>
+  <Objects>
+    <Sphere id="1"><Material>2</Material><Center>4</Center><Radius>0.25</Radius></Sphere>
+    <Triangle id="1"><Material>1</Material><Indices>1 2 3</Indices></Triangle>
+    <Mesh id="1"><Material>2</Material><Faces>1 2 3
+        3 2 1</Faces></Mesh>
+  </Objects>
+</Scene>"""
+
+
+def test_xml_loader_semantics(tmp_path):
+    p = tmp_path / "mini.xml"
+    p.write_text(MINI)
+    sc = H.load_scene_xml(str(p))
+    d = sc.desc
+    # defaults (parser.cpp:24-57): BackgroundColor "0 0 0", ShadowRayEpsilon 0.001
+    assert list(d.background) == [0, 0, 0]
+    assert d.shadow_ray_epsilon == np.float32(0.001)
+    assert d.max_recursion_depth == 3
+    # children are found by name, whatever their order; ids are ignored
+    cam, name = sc.cameras[0]
+    assert name == "a.ppm" and (cam.image_width, cam.image_height) == (4, 2)
+    assert (cam.position.x, cam.position.y, cam.position.z) == (1, 2, 3) and cam.near_distance == 1.5
+    assert (cam.l, cam.r, cam.b, cam.t) == (-1, 1, -0.5, 0.5)
+    assert sc.materials["is_mirror"].tolist() == [1, 0]
+    assert sc.materials["f"][0, 12] == 3 and sc.materials["f"][0, 9:12].tolist() == [0.5, 0.5, 0.5]
+    assert sc.lights[0, 3] == 1000.0
+    # flat triangle list: <Triangle>s first, then mesh faces (raytracer.cpp:336-341), whatever the file order
+    assert sc.triangles.tolist() == [[1, 2, 3, 1], [1, 2, 3, 2], [3, 2, 1, 2]]
+    assert sc.spheres["center_vertex_id"].tolist() == [4] and sc.spheres["radius"].tolist() == [0.25]
+    assert len(sc.vertices) == 4
+
+
+def test_xml_loader_errors(tmp_path):
+    with pytest.raises(RuntimeError, match="cannot be loaded"):
+        H.load_scene_xml(str(tmp_path / "missing.xml"))
+    p = tmp_path / "bad.xml"
+    p.write_text("<Scene><Cameras></Cameras></Scene>")
+    with pytest.raises(RuntimeError, match="Lights"):
+        H.load_scene_xml(str(p))
+    p.write_text("   ")
+    with pytest.raises(RuntimeError, match="Root is not found"):
+        H.load_scene_xml(str(p))
+
+
+def test_ppm_writer_format(tmp_path):
+    img = np.array([[[0, 1, 22], [255, 100, 9]], [[7, 8, 9], [10, 11, 12]]], np.uint8)
+    p = str(tmp_path / "x.ppm")
+    H.write_ppm(p, img)
+    # ppm.cpp:13-35: "%d " per channel, the last value of a row without the space, "\n" per row
+    assert open(p, "rb").read() == b"P3\n2 2\n255\n0 1 22 255 100 9\n7 8 9 10 11 12\n"
+    with pytest.raises(RuntimeError, match="cannot be opened"):
+        H.write_ppm(str(tmp_path / "no_such_dir" / "x.ppm"), img)
+
+
+@pytest.mark.parametrize("key", ["simple.aa1", "horse_and_mug.aa1"])
+def test_ppm_writer_md5_of_reference_output(key, tmp_path):
+    """ppm_md5 is the md5 of the file the reference's own write_ppm produced for this frame."""
+    img, m = H.golden_image(key)
+    p = str(tmp_path / "g.ppm")
+    H.write_ppm(p, img)
+    assert hashlib.md5(open(p, "rb").read()).hexdigest() == m["ppm_md5"]
+
+
+def _f32(bits):
+    return struct.unpack("<f", struct.pack("<I", bits & 0xFFFFFFFF))[0]
+
+
+def test_specular_gate_closed_form_equals_libm():
+    """cos >= 0xB90665D3 && cos <= 1  <=>  (float)(acos(cos)*180/3.1415) <= 90.01  (raytracer.cpp:411-412)."""
+    L = H.rt_b200.cuda_lib()
+    L.rt_host_specular_gate.argtypes = [C.c_float]
+    O = H.oracle_lib()
+    thr = 0xB90665D3
+    cases = [_f32(thr + k) for k in range(-3000, 3001)]  # negative floats: larger bits = more negative
+    cases += [_f32(0x3F800000 + k) for k in range(-50, 51)]  # around +1
+    cases += [0.0, -0.0, 1.0, -1.0, 2.0, -2.0, float("nan"), float("inf"), float("-inf"), 1e-30, -1e-30, 0.5, -0.5]
+    rng = np.random.default_rng(1)
+    cases += rng.uniform(-1.2, 1.2, 20000).astype(np.float32).tolist()
+    cases += (rng.uniform(-1, 1, 20000) * 1e-3).astype(np.float32).tolist()
+    for c in cases:
+        assert L.rt_host_specular_gate(c) == O.or_specular_gate(c), c
+
+
+def test_integer_pow_chain_equals_libm_after_narrowing():
+    """pow_ref's square-and-multiply in double vs libm pow, both narrowed to float, on the shipped exponents."""
+    import math
+    L = H.rt_b200.cuda_lib()
+    L.rt_host_pow_ref.argtypes = [C.c_float, C.c_float]
+    L.rt_host_pow_ref.restype = C.c_float
+    rng = np.random.default_rng(2)
+    bases = np.concatenate([rng.uniform(0, 1, 4000), 1 - rng.uniform(0, 1, 2000) ** 4 * 0.05, [0.0, 1.0]]).astype(np.float32)
+    diffs = 0
+    for e in (0.0, 1.0, 3.0, 50.0, 100.0, 2.5):
+        for b in bases:
+            want = np.float32(math.pow(float(b), e))
+            got = np.float32(L.rt_host_pow_ref(float(b), e))
+            if want != got:
+                diffs += 1
+                assert abs(float(want) - float(got)) <= np.spacing(want), (b, e, want, got)
+    assert diffs <= 2  # a ~1e-7 sliver by construction; none expected in 36 000 draws
+
+
+@pytest.mark.parametrize("scene", ["simple", "cornellbox", "marbles", "bunny", "horse_and_mug", "low_poly"])
+def test_host_bvh_invariants(scene):
+    L = H.rt_b200.cuda_lib()
+    L.rt_host_check_bvh.argtypes = [C.POINTER(H.RtSceneDesc), C.POINTER(C.c_float), C.POINTER(C.c_int32)]
+    sc = H.golden_scene(scene)
+    cost, depth = C.c_float(), C.c_int32()
+    n = L.rt_host_check_bvh(C.byref(sc.desc), C.byref(cost), C.byref(depth))
+    assert n >= 1, L.rt_last_error()
+    assert 0 < depth.value <= 60 and cost.value > 0
