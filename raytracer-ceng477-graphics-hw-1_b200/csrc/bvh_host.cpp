@@ -191,7 +191,12 @@ float bvh_sah_cost(const HostBvh &bvh) {
     const float ra = half_area(root);
     if (!(ra > 0)) return 0;
     double cost = kCostNode;  // the root step
-    for (auto &n: bvh.nodes) {
+    std::vector<int> todo(1, 0);  // reachable nodes only (the GPU builder leaves collapsed subtrees behind)
+    while (!todo.empty()) {
+        const HostNode &n = bvh.nodes[todo.back()];
+        todo.pop_back();
+        if (n.child0 >= 0 && n.child0 != kEmptyChild) todo.push_back(n.child0);
+        if (n.child1 >= 0 && n.child1 != kEmptyChild) todo.push_back(n.child1);
         const float *mns[2] = {n.c0mn, n.c1mn}, *mxs[2] = {n.c0mx, n.c1mx};
         const int ch[2] = {n.child0, n.child1};
         for (int c = 0; c < 2; c++) {

@@ -310,7 +310,10 @@ RT_DEV unsigned quantise(float c) { return (unsigned) (unsigned char) roundf(cla
 constexpr int kThreads = 256;
 constexpr int kMaxP = RT_TILE;  // output pixels per work-item side never exceed one tile
 
-__global__ void __launch_bounds__(kThreads, 2) render_kernel(const __grid_constant__ RenderParams p) {
+#ifndef RT_MIN_CTAS
+#define RT_MIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(kThreads, RT_MIN_CTAS) render_kernel(const __grid_constant__ RenderParams p) {
     __shared__ unsigned acc[kMaxP * kMaxP * 3];
     __shared__ unsigned s_item;
 

@@ -230,7 +230,7 @@ def cuda_lib():
     """libwhitted_b200.so; raises if it has not been built (no fallback)."""
     global _cuda
     if _cuda is None:
-        path = os.path.join(PKG, "libwhitted_b200.so")
+        path = os.environ.get("RT_B200_LIB") or os.path.join(PKG, "libwhitted_b200.so")  # env override: A/B kernel experiments
         if not os.path.exists(path):
             raise RtError(f"{path} is missing: build it with `make -C {PKG}` (or __graft_entry__.build())")
         L = C.CDLL(path)
