@@ -3,6 +3,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -19,6 +20,10 @@ int launch_render(const RenderParams &p, int n_ctas, cudaStream_t stream);
 int launch_assemble(const unsigned char *parts, long long part_stride, int part_world, int nx, int ny, int tiles_x,
                     int n_tiles, unsigned char *frame, cudaStream_t stream);
 int render_kernel_occupancy(int *ctas_per_sm);
+int launch_render_v2(const RenderParams &p, int n_ctas, cudaStream_t stream);
+int render_kernel_v2_occupancy(int *ctas_per_sm, int *warps_per_cta);
+int launch_render_v3(const RenderParams &p, int n_ctas, cudaStream_t stream);
+int render_kernel_v3_occupancy(int *ctas_per_sm, int *warps_per_cta);
 int build_bvh_lbvh_device(const std::vector<Aabb> &bounds, HostBvh &out, float *ms_device);
 }  // namespace rtb
 
@@ -28,7 +33,12 @@ struct RtScene {
     int device = 0;
     int n_sms = 0;
     int ctas_per_sm = 1;
+    int kernel = 2;  // 1: CTA-tile megakernel (render.cu), 2: warp-tile state machine (render_v2.cu); env RT_B200_KERNEL
+    int ctas_per_sm2 = 1, warps_per_cta2 = 4;
+    int refill_threshold = 0;  // env RT_B200_REFILL
+    int ctas_per_sm3 = 1, warps_per_cta3 = 4;
     // device buffers
+    float4 *d_tri_nn = nullptr;
     float4 *d_nodes = nullptr, *d_prims = nullptr, *d_tri_nm = nullptr, *d_sph_cr = nullptr, *d_materials = nullptr,
            *d_lights = nullptr;
     int *d_sph_mat = nullptr;
@@ -187,10 +197,23 @@ int enqueue_part(RtScene *s, const RtCamera *cam, int aa, int rank, int world, u
     p.nx = cam->image_width;
     p.ny = cam->image_height;
     p.f = aa;
-    // work item: P x P output pixels with P*f ~ 32 sub-samples a side (1024 sub-samples, 4 per thread)
+    // work item: P x P output pixels with P*f ~ 32 sub-samples a side (1024 sub-samples): a CTA tile with 4
+    // sub-samples per thread (kernel 1) or a warp tile refilled lane by lane (kernel 2, P <= 16 when f > 1)
     int P = (32 + aa - 1) / aa;
     if (P > RT_TILE) P = RT_TILE;
     if (P < 1) P = 1;
+    if (s->kernel >= 2) {
+        if (aa > 1 && P > 16) P = 16;
+        // small frames: shrink the warp tile (down to 8 sub-samples a side) until there are enough tiles to
+        // give every resident warp a few dozen of them (dynamic load balance: tiles differ a lot in cost)
+        const long long slots = s->kernel == 2 ? (long long) s->n_sms * s->ctas_per_sm2 * s->warps_per_cta2
+                                               : (long long) s->n_sms * s->ctas_per_sm3 * s->warps_per_cta3;
+        for (;;) {
+            const long long ix = (RT_TILE + P - 1) / P;
+            if (part_tiles(g, rank, world) * ix * ix >= 32 * slots || P * aa <= 8 || P == 1) break;
+            P = (P + 1) / 2;
+        }
+    }
     p.P = P;
     p.items_x = (RT_TILE + P - 1) / P;
     p.tiles_x = g.tiles_x;
@@ -201,15 +224,29 @@ int enqueue_part(RtScene *s, const RtCamera *cam, int aa, int rank, int world, u
     if (n_items >= (1LL << 32) - (1 << 22)) return fail(RT_ERR_INVALID, "too many work items");
     p.n_items = (unsigned) n_items;
     p.out_mode = out_mode;
+    p.refill_threshold = s->refill_threshold;
     p.out = d_out;
     p.work_counter = s->d_counter;
     p.stats = s->d_stats;
     CU(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned int), stream));
     CU(cudaMemsetAsync(s->d_stats, 0, 4 * sizeof(unsigned long long), stream));
     if (n_items == 0) return RT_OK;
-    long long ctas = (long long) s->n_sms * s->ctas_per_sm;
-    if (ctas > n_items) ctas = n_items;
-    cudaError_t e = (cudaError_t) launch_render(p, (int) ctas, stream);
+    cudaError_t e;
+    if (s->kernel == 2) {
+        long long ctas = (long long) s->n_sms * s->ctas_per_sm2;
+        const long long need = (n_items + s->warps_per_cta2 - 1) / s->warps_per_cta2;
+        if (ctas > need) ctas = need;
+        e = (cudaError_t) launch_render_v2(p, (int) ctas, stream);
+    } else if (s->kernel == 3) {
+        long long ctas = (long long) s->n_sms * s->ctas_per_sm3;
+        const long long need = (n_items + s->warps_per_cta3 - 1) / s->warps_per_cta3;
+        if (ctas > need) ctas = need;
+        e = (cudaError_t) launch_render_v3(p, (int) ctas, stream);
+    } else {
+        long long ctas = (long long) s->n_sms * s->ctas_per_sm;
+        if (ctas > n_items) ctas = n_items;
+        e = (cudaError_t) launch_render(p, (int) ctas, stream);
+    }
     if (e != cudaSuccess) return fail(RT_ERR_CUDA, std::string("render kernel launch: ") + cudaGetErrorString(e));
     if (launches) (*launches)++;
     return RT_OK;
@@ -392,7 +429,7 @@ int rt_scene_create(const RtSceneDesc *desc, const RtBuildOptions *opts, RtScene
             prims[3 * (size_t) sidx + 2] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
-    std::vector<float4> tri_nm((size_t) nt);
+    std::vector<float4> tri_nm((size_t) nt), tri_nn((size_t) nt);
     for (int i = 0; i < nt; i++) {
         const RtTriangle &t = desc->triangles[i];
         const RtVec3 &a = desc->vertices[t.v0_id - 1], &b = desc->vertices[t.v1_id - 1], &c = desc->vertices[t.v2_id - 1];
@@ -406,6 +443,13 @@ int rt_scene_create(const RtSceneDesc *desc, const RtBuildOptions *opts, RtScene
         s2 = s2 + zz;
         const float len = (float) std::sqrt((double) s2);
         tri_nm[i] = make_float4(nx / len, ny / len, nz / len, bits(t.material_id));
+        // intersection.normal.normalize() of an already unit-length normal (raytracer.cpp:414, :432): same ops, once
+        volatile float ux = nx / len, uy = ny / len, uz = nz / len;
+        volatile float uxx = ux * ux, uyy = uy * uy, uzz = uz * uz;
+        volatile float u2 = uxx + uyy;
+        u2 = u2 + uzz;
+        const float ulen = (float) std::sqrt((double) u2);
+        tri_nn[i] = make_float4(ux / ulen, uy / ulen, uz / ulen, 0.f);
     }
     std::vector<float4> sph_cr((size_t) ns);
     std::vector<int> sph_mat((size_t) ns);
@@ -433,6 +477,7 @@ int rt_scene_create(const RtSceneDesc *desc, const RtBuildOptions *opts, RtScene
     rc = upload(&s->d_nodes, nodes.data(), nodes.size());
     if (rc == RT_OK) rc = upload(&s->d_prims, prims.data(), prims.size());
     if (rc == RT_OK) rc = upload(&s->d_tri_nm, tri_nm.data(), tri_nm.size());
+    if (rc == RT_OK) rc = upload(&s->d_tri_nn, tri_nn.data(), tri_nn.size());
     if (rc == RT_OK) rc = upload(&s->d_sph_cr, sph_cr.data(), sph_cr.size());
     if (rc == RT_OK) rc = upload(&s->d_sph_mat, sph_mat.data(), sph_mat.size());
     if (rc == RT_OK) rc = upload(&s->d_ranks, ranks.data(), ranks.size());
@@ -447,6 +492,17 @@ int rt_scene_create(const RtSceneDesc *desc, const RtBuildOptions *opts, RtScene
         int occ = 0;
         if (render_kernel_occupancy(&occ) != 0 || occ < 1) rc = fail(RT_ERR_CUDA, "render kernel cannot be resident on this device (built for sm_100a)");
         s->ctas_per_sm = occ;
+        int occ2 = 0;
+        if (render_kernel_v2_occupancy(&occ2, &s->warps_per_cta2) != 0 || occ2 < 1) rc = fail(RT_ERR_CUDA, "render kernel v2 cannot be resident on this device");
+        s->ctas_per_sm2 = occ2;
+        const char *kv = getenv("RT_B200_KERNEL");
+        if (kv && kv[0] == '1') s->kernel = 1;
+        if (kv && kv[0] == '3') s->kernel = 3;
+        int occ3 = 0;
+        if (render_kernel_v3_occupancy(&occ3, &s->warps_per_cta3) != 0 || occ3 < 1) rc = fail(RT_ERR_CUDA, "render kernel v3 cannot be resident on this device");
+        s->ctas_per_sm3 = occ3;
+        const char *rv = getenv("RT_B200_REFILL");
+        if (rv) s->refill_threshold = atoi(rv);
     }
     if (rc != RT_OK) {
         rt_scene_destroy(s);
@@ -457,6 +513,7 @@ int rt_scene_create(const RtSceneDesc *desc, const RtBuildOptions *opts, RtScene
     b.nodes = s->d_nodes;
     b.prims = s->d_prims;
     b.tri_nm = s->d_tri_nm;
+    b.tri_nn = s->d_tri_nn;
     b.sph_cr = s->d_sph_cr;
     b.sph_mat = s->d_sph_mat;
     b.ranks = s->d_ranks;
@@ -498,6 +555,7 @@ void rt_scene_destroy(RtScene *s) {
     cudaFree(s->d_nodes);
     cudaFree(s->d_prims);
     cudaFree(s->d_tri_nm);
+    cudaFree(s->d_tri_nn);
     cudaFree(s->d_sph_cr);
     cudaFree(s->d_sph_mat);
     cudaFree(s->d_ranks);

@@ -15,121 +15,9 @@
 #include <cfloat>
 #include <cstdint>
 
-#include "exact_math.h"
-#include "render_params.h"
-#include "rt_b200.h"
-#include "rt_internal.h"
+#include "device_common.cuh"
 
 namespace rtb {
-
-struct V3 {
-    float x, y, z;
-};
-
-#define RT_DEV __device__ __forceinline__
-
-RT_DEV V3 mk(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
-RT_DEV V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
-RT_DEV V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
-RT_DEV V3 operator-(V3 a) { return mk(-a.x, -a.y, -a.z); }
-RT_DEV V3 operator*(V3 a, float f) { return mk(a.x * f, a.y * f, a.z * f); }
-RT_DEV V3 operator/(V3 a, float f) { return mk(a.x / f, a.y / f, a.z / f); }
-RT_DEV float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }  // (x*x + y*y) + z*z, parser.h:30-32
-RT_DEV V3 mulv(V3 a, V3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }   // dotWithoutSum, parser.h:46-48
-RT_DEV float length(V3 a) { return sqrtf(a.x * a.x + a.y * a.y + a.z * a.z); }  // == (float)sqrt((double)s), parser.h:77-79
-RT_DEV V3 normalize(V3 a) { float l = length(a); return mk(a.x / l, a.y / l, a.z / l); }  // parser.h:72-75
-RT_DEV V3 ld3(const float *p) { return mk(p[0], p[1], p[2]); }
-RT_DEV V3 xyz(float4 q) { return mk(q.x, q.y, q.z); }
-// std::min / std::max as libstdc++ defines them (NaN handling differs from fminf/fmaxf)
-RT_DEV float std_min(float a, float b) { return (b < a) ? b : a; }
-RT_DEV float std_max(float a, float b) { return (a < b) ? b : a; }
-RT_DEV float clamp_ref(float x, float a, float b) { return std_max(a, std_min(x, b)); }  // parser.h:81-86
-
-struct Ray {
-    V3 o, d;
-    V3 inv;  // finite reciprocal used by the box test only
-    V3 ood;  // o * inv
-    int oct; // bit a <=> d[a] > 0 (raytracer.cpp:190)
-};
-
-RT_DEV float finite_rcp(float d) {
-    float r = 1.0f / d;
-    return (fabsf(r) <= 1e18f) ? r : copysignf(1e18f, r);  // also catches inf; r is never NaN for finite d
-}
-
-RT_DEV Ray make_ray(V3 o, V3 d) {
-    Ray r;
-    r.o = o;
-    r.d = d;
-    r.inv = mk(finite_rcp(d.x), finite_rcp(d.y), finite_rcp(d.z));
-    r.ood = mk(o.x * r.inv.x, o.y * r.inv.y, o.z * r.inv.z);
-    r.oct = (d.x > 0.0f ? 1 : 0) | (d.y > 0.0f ? 2 : 0) | (d.z > 0.0f ? 4 : 0);
-    return r;
-}
-
-// Cramer's rule exactly as raytracer.cpp:129-175 evaluates it (det() at :15-19), with the shared
-// 2x2 minors written once: identical products and differences give identical bits.
-//   q0 = a, q1 = a-b, q2 = a-c and q2.w = (a-b).y*(a-c).z - (a-c).y*(a-b).z
-RT_DEV bool hit_triangle(const Ray &r, float4 q0, float4 q1, float4 q2, float &t_out) {
-    const float abx = q1.x, aby = q1.y, abz = q1.z;
-    const float acx = q2.x, acy = q2.y, acz = q2.z, mn = q2.w;
-    const float dx = r.d.x, dy = r.d.y, dz = r.d.z;
-    const float aox = q0.x - r.o.x, aoy = q0.y - r.o.y, aoz = q0.z - r.o.z;
-    const float m1 = acy * dz - dy * acz;
-    const float m2 = aby * dz - dy * abz;
-    const float m3 = aoy * dz - dy * aoz;
-    const float detA = abx * m1 - acx * m2 + dx * mn;
-    const float m4 = aoy * acz - acy * aoz;
-    const float beta = (aox * m1 - acx * m3 + dx * m4) / detA;
-    const float m5 = aby * aoz - aoy * abz;
-    const float gamma = (abx * m3 - aox * m2 + dx * m5) / detA;
-    const float alpha = 1.0f - beta - gamma;
-    if (!(alpha >= 0.0f && beta >= 0.0f && gamma >= 0.0f)) return false;
-    const float m6 = acy * aoz - aoy * acz;
-    const float t = (abx * m6 - acx * m5 + aox * mn) / detA;
-    t_out = t;
-    return t >= 0.0f;
-}
-
-// raytracer.cpp:70-96; roots in double exactly where the reference promotes.
-RT_DEV bool hit_sphere(const Ray &r, V3 c, float rad, float &t_out) {
-    const V3 oc = r.o - c;
-    const float B = 2.0f * dot(r.d, oc);
-    const float A = dot(r.d, r.d);
-    const float C = dot(oc, oc) - rad * rad;
-    const float disc = B * B - 4.0f * A * C;
-    if (!(disc >= 0.0f)) return false;
-    const double sq = sqrt((double) disc);
-    const double den = (double) (2.0f * A);
-    const float t1 = (float) ((-(double) B - sq) / den);
-    const float t2 = (float) ((-(double) B + sq) / den);
-    if (t1 < 0.0f && t2 < 0.0f) return false;
-    t_out = t1;  // tSmall = t1 even when negative (origin inside the sphere)
-    return true;
-}
-
-RT_DEV void slab(const Ray &r, float mnx, float mxx, float mny, float mxy, float mnz, float mxz, float &tmin, float &tmax) {
-    const float x0 = __fmaf_rn(mnx, r.inv.x, -r.ood.x), x1 = __fmaf_rn(mxx, r.inv.x, -r.ood.x);
-    const float y0 = __fmaf_rn(mny, r.inv.y, -r.ood.y), y1 = __fmaf_rn(mxy, r.inv.y, -r.ood.y);
-    const float z0 = __fmaf_rn(mnz, r.inv.z, -r.ood.z), z1 = __fmaf_rn(mxz, r.inv.z, -r.ood.z);
-    tmin = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1));
-    tmax = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
-}
-
-constexpr int kStackSize = 64;
-constexpr int kSentinel = 0x7ffffffe;
-
-// One primitive against the ray.  Returns true when the primitive reports an intersection.
-RT_DEV bool hit_prim(const RenderParams &p, const Ray &r, int slot, float &t, int &prim) {
-    const float4 q0 = __ldg(&p.prims[3 * slot]);
-    const float4 q1 = __ldg(&p.prims[3 * slot + 1]);
-    prim = __float_as_int(q0.w);
-    if (__float_as_int(q1.w) == 0) {
-        const float4 q2 = __ldg(&p.prims[3 * slot + 2]);
-        return hit_triangle(r, q0, q1, q2, t);
-    }
-    return hit_sphere(r, xyz(q0), q1.x, t);
-}
 
 // Closest hit: argmin over all reported intersections of (t, reference visit rank).
 // ANY: true as soon as some primitive reports t < limit (raytracer.cpp:237, 245).
@@ -207,10 +95,6 @@ RT_DEV bool traverse(const RenderParams &p, const Ray &r, float limit, float &tb
     return pbest >= 0;
 }
 
-struct Counters {
-    unsigned primary, reflection, shadow, occluded;
-};
-
 // rayTrace (raytracer.cpp:385-452) with the recursion unrolled into a loop: every mirror level
 // pushes its local colour and material; the result is folded back to front so that each level's
 // `clamp(local + reflected * km)` rounds exactly like the recursive original.
@@ -254,7 +138,7 @@ RT_DEV V3 trace_path(const RenderParams &p, V3 o, V3 d, Counters &cnt) {
         const V3 P = o + d * t;
         const V3 Pe = P + n * p.eps;  // raytracer.cpp:397
         const V3 dn = normalize(d);
-        const V3 nn = normalize(n);
+        const V3 nn = prim < p.n_tris ? xyz(__ldg(&p.tri_nn[prim])) : normalize(n);
 
         for (int li = 0; li < p.n_lights; li++) {  // raytracer.cpp:399-427
             const V3 lpos = xyz(__ldg(&p.lights[2 * li]));
@@ -303,9 +187,6 @@ RT_DEV V3 trace_path(const RenderParams &p, V3 o, V3 d, Counters &cnt) {
     }
     return result;
 }
-
-// parser.h:88-93
-RT_DEV unsigned quantise(float c) { return (unsigned) (unsigned char) roundf(clamp_ref(c, 0.0f, 255.0f)); }
 
 constexpr int kThreads = 256;
 constexpr int kMaxP = RT_TILE;  // output pixels per work-item side never exceed one tile
@@ -418,6 +299,127 @@ __global__ void __launch_bounds__(kThreads, RT_MIN_CTAS) render_kernel(const __g
         atomicAdd(&p.stats[2], (unsigned long long) v2);
         atomicAdd(&p.stats[3], (unsigned long long) v3);
     }
+}
+
+// ---- kernel 3: the same per-lane code (trace_path), but WARP-granular ---------------------------
+// One warp claims a warp tile (P x P output pixels) from the global counter and walks its sub-samples
+// 32 at a time in 8x4 blocks; SSAA sums live in warp-private shared memory.  No CTA barrier: warps
+// never wait for each other, and small frames still produce enough independent work items.
+constexpr int kWarps3 = 4;
+constexpr int kThreads3 = kWarps3 * 32;
+constexpr int kMaxP3 = 16;
+#ifndef RT_MIN_CTAS3
+#define RT_MIN_CTAS3 6
+#endif
+
+__global__ void __launch_bounds__(kThreads3, RT_MIN_CTAS3) render_kernel_v3(const __grid_constant__ RenderParams p) {
+    __shared__ unsigned acc_all[kWarps3][kMaxP3 * kMaxP3 * 3];
+    const int lane = threadIdx.x & 31;
+    unsigned *acc = acc_all[threadIdx.x >> 5];
+    const int f = p.f, P = p.P;
+    const int items_per_tile = p.items_x * p.items_x;
+    const bool warp_in_one_pixel = (f % 8) == 0;
+    Counters cnt = {0u, 0u, 0u, 0u};
+    const V3 E0 = ld3(p.e), Q = ld3(p.q), U = ld3(p.u), Vv = ld3(p.v);
+
+    for (;;) {
+        unsigned item = 0;
+        if (lane == 0) item = atomicAdd(p.work_counter, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= p.n_items) break;
+        const int local_tile = (int) (item / (unsigned) items_per_tile);
+        const int sub = (int) (item % (unsigned) items_per_tile);
+        const int tile = p.part_rank + local_tile * p.part_world;
+        const int tx0 = (tile % p.tiles_x) * RT_TILE, ty0 = (tile / p.tiles_x) * RT_TILE;
+        const int ix0 = (sub % p.items_x) * P, iy0 = (sub / p.items_x) * P;
+        const int px0 = tx0 + ix0, py0 = ty0 + iy0;
+        const int pw = max(0, min(min(P, RT_TILE - ix0), p.nx - px0));
+        const int ph = max(0, min(min(P, RT_TILE - iy0), p.ny - py0));
+        if (pw == 0 || ph == 0) continue;
+        const int sw = pw * f, sh = ph * f;
+        const int nbx = (sw + 7) >> 3, nby = (sh + 3) >> 2;
+        const int total = nbx * nby * 32;
+        if (f > 1) {
+            for (int i = lane; i < pw * ph * 3; i += 32) acc[i] = 0u;
+            __syncwarp();
+        }
+        for (int slot = lane; slot < total; slot += 32) {
+            const int b = slot >> 5;
+            const int lx = (b % nbx) * 8 + (lane & 7);
+            const int ly = (b / nbx) * 4 + (lane >> 3);
+            const bool valid = lx < sw && ly < sh;
+            unsigned r8 = 0, g8 = 0, b8 = 0;
+            if (valid) {
+                const float su = ((float) (px0 * f + lx) + 0.5f) * p.su_mul;
+                const float sv = ((float) (py0 * f + ly) + 0.5f) * p.sv_mul;
+                const V3 s = (Q + U * su) - Vv * sv;
+                const V3 c = trace_path(p, E0, s - E0, cnt);
+                r8 = quantise(c.x);
+                g8 = quantise(c.y);
+                b8 = quantise(c.z);
+            }
+            if (f == 1) {
+                if (valid) {
+                    unsigned char *o;
+                    if (p.out_mode == kOutFrame) o = p.out + ((size_t) (py0 + ly) * p.nx + (px0 + lx)) * 3;
+                    else o = p.out + (((size_t) local_tile * RT_TILE + (iy0 + ly)) * RT_TILE + (ix0 + lx)) * 3;
+                    o[0] = (unsigned char) r8;
+                    o[1] = (unsigned char) g8;
+                    o[2] = (unsigned char) b8;
+                }
+            } else if (warp_in_one_pixel) {
+                r8 = __reduce_add_sync(0xffffffffu, r8);
+                g8 = __reduce_add_sync(0xffffffffu, g8);
+                b8 = __reduce_add_sync(0xffffffffu, b8);
+                if (lane == 0 && valid) {
+                    unsigned *a = &acc[((ly / f) * pw + (lx / f)) * 3];
+                    a[0] += r8;
+                    a[1] += g8;
+                    a[2] += b8;
+                }
+            } else if (valid) {
+                unsigned *a = &acc[((ly / f) * pw + (lx / f)) * 3];
+                atomicAdd(a, r8);
+                atomicAdd(a + 1, g8);
+                atomicAdd(a + 2, b8);
+            }
+        }
+        if (f > 1) {
+            __syncwarp();
+            const unsigned ff = (unsigned) (f * f);
+            for (int i = lane; i < pw * ph; i += 32) {
+                const int x = i % pw, y = i / pw;
+                const unsigned *a = &acc[i * 3];
+                unsigned char *o;
+                if (p.out_mode == kOutFrame) o = p.out + ((size_t) (py0 + y) * p.nx + (px0 + x)) * 3;
+                else o = p.out + (((size_t) local_tile * RT_TILE + (iy0 + y)) * RT_TILE + (ix0 + x)) * 3;
+                o[0] = (unsigned char) (a[0] / ff);
+                o[1] = (unsigned char) (a[1] / ff);
+                o[2] = (unsigned char) (a[2] / ff);
+            }
+            __syncwarp();
+        }
+    }
+    unsigned v0 = __reduce_add_sync(0xffffffffu, cnt.primary);
+    unsigned v1 = __reduce_add_sync(0xffffffffu, cnt.reflection);
+    unsigned v2 = __reduce_add_sync(0xffffffffu, cnt.shadow);
+    unsigned v3 = __reduce_add_sync(0xffffffffu, cnt.occluded);
+    if (lane == 0) {
+        atomicAdd(&p.stats[0], (unsigned long long) v0);
+        atomicAdd(&p.stats[1], (unsigned long long) v1);
+        atomicAdd(&p.stats[2], (unsigned long long) v2);
+        atomicAdd(&p.stats[3], (unsigned long long) v3);
+    }
+}
+
+int launch_render_v3(const RenderParams &p, int n_ctas, cudaStream_t stream) {
+    render_kernel_v3<<<n_ctas, kThreads3, 0, stream>>>(p);
+    return (int) cudaGetLastError();
+}
+
+int render_kernel_v3_occupancy(int *ctas_per_sm, int *warps_per_cta) {
+    *warps_per_cta = kWarps3;
+    return (int) cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, render_kernel_v3, kThreads3, 0);
 }
 
 // Gathering GPU: scatter `part_world` packed tile buffers into the row-major frame.

@@ -17,6 +17,7 @@ struct RenderParams {
     const float4 *nodes;
     const float4 *prims;
     const float4 *tri_nm;
+    const float4 *tri_nn;  // normalize(normal) per triangle (raytracer.cpp:414, 432 re-normalise the stored normal)
     const float4 *sph_cr;
     const int *sph_mat;
     const uint32_t *ranks;
@@ -40,6 +41,7 @@ struct RenderParams {
     int part_rank, part_world;
     unsigned int n_items;  // work items of this part
     int out_mode;
+    int refill_threshold;  // kernel 2: refill idle lanes once <= this many lanes are busy
     unsigned char *out;
     unsigned int *work_counter;      // zeroed before launch
     unsigned long long *stats;       // [4] primary, reflection, shadow, occluded

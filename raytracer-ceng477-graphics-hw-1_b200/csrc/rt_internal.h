@@ -27,6 +27,7 @@ namespace rtb {
 //                                             [1] = radius 0 0 bits(1)
 //                                   prim_id: triangles 0..nt-1 in the reference's list order, spheres nt..nt+ns-1
 //  tri_nm     float4[nt]            unit geometric normal (raytracer.cpp:346) + bits(material_id)
+//  tri_nn     float4[nt]            the stored normal normalised once more (what raytracer.cpp:414/:432 compute per hit)
 //  sph_cr     float4[ns]            centre + radius; sph_mat int[ns]
 //  ranks      uint32[8 * n_prims]   visit rank of prim_id in the reference's traversal order for each
 //                                   ray-direction sign octant (bit a <=> dir[a] > 0) — exact-t tie breaking

@@ -14,6 +14,11 @@ What it writes
                                  selected OUTPUT rows of the 7680x3840 16x16-SSAA frame (config 5), built
                                  from the reference's own sub-samples (ref_time_rows) and the integer
                                  average of raytracer.cpp:466-477
+  images/horse_and_mug_8k.aa16.full.rgb.xz
+                                 the whole config-5 frame (only with --full-8k: ~25 min of CPU).  The reference cannot
+                                 render it as written (int overflow, raytracer.cpp:363), so the oracle renders it and
+                                 the result is accepted only if its P3 md5 equals the md5 of the reference's 64-bit-index
+                                 build recorded in SURVEY.md 8c (2be09d2f...) and its ray counts equal SURVEY.md 8d
   manifest.json                  sizes, md5 of the P3 text the reference's write_ppm emits, sha256 of the
                                  raw frames, loader digests, reference BVH statistics, and the oracle's
                                  ray counters (known answers for the GPU's device counters)
@@ -124,6 +129,28 @@ def main():
                                                 "shadow": 12646772572}}
         orc.close()
         ref.close()
+    full_key = "horse_and_mug_8k.aa16.full"
+    if "--full-8k" in sys.argv:
+        sc = H.load_scene_xml(H.golden_scene_path("horse_and_mug"))
+        img, st = H.OracleScene(sc).render(sc.camera(0, 7680, 3840), 16)
+        with tempfile.NamedTemporaryFile(suffix=".ppm") as f:
+            H.write_ppm(f.name, img)
+            md5 = hashlib.md5(open(f.name, "rb").read()).hexdigest()
+        assert md5 == "2be09d2f9bf003086286f36f4ee9cad0", md5
+        assert (st.primary_rays, st.reflection_rays, st.shadow_rays) == (7549747200, 5797408973, 12646772572)
+        with open(os.path.join(HERE, "images", full_key + ".rgb.xz"), "wb") as fo:
+            fo.write(lzma.compress(img.tobytes(), preset=6))
+        manifest["images"][full_key] = {"scene": "horse_and_mug", "camera": 0, "aa": 16, "width": 7680, "height": 3840,
+                                        "rgb_sha256": hashlib.sha256(img.tobytes()).hexdigest(), "ppm_md5": md5, "slow": True,
+                                        "rays": {"primary": st.primary_rays, "reflection": st.reflection_rays,
+                                                 "shadow": st.shadow_rays, "shadow_occluded": st.shadow_occluded}}
+    else:  # keep the entry of an earlier --full-8k run
+        try:
+            old = json.load(open(os.path.join(HERE, "manifest.json")))["images"].get(full_key)
+            if old:
+                manifest["images"][full_key] = old
+        except Exception:
+            pass
     with open(os.path.join(HERE, "manifest.json"), "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
     print("done")

@@ -11,7 +11,7 @@ import harness as H
 
 pytestmark = pytest.mark.gpu
 
-ALL_IMAGES = sorted(k for k, v in H.manifest()["images"].items() if "rows" not in v)
+ALL_IMAGES = sorted(k for k, v in H.manifest()["images"].items() if "rows" not in v and not v.get("slow"))
 
 _tracers = {}
 
@@ -110,3 +110,44 @@ def test_gpu_lbvh_builder(key):
           f"build {inf.ms_build_device:.3f} ms device, {rt.last_stats.ms_render:.3f} ms render | sah_host: {ref_inf.bvh_nodes} nodes "
           f"sah {ref_inf.bvh_sah_cost:.1f} build {ref_inf.ms_build_host:.1f} ms host")
     assert np.array_equal(img, gold)
+
+
+@pytest.mark.slow
+def test_full_size_config5(tmp_path):
+    """BASELINE.json config 5 at full size: horse_and_mug 7680x3840, 16x16 SSAA (25.99 G rays, ~1 s on a B200).
+    Known answers: the reference's ray counts and the md5 of its PPM (64-bit-index build), and
+    12 output rows rebuilt from the reference's own sub-samples (tests/golden/make_golden.py)."""
+    import hashlib
+    gold, m = H.golden_image("horse_and_mug_8k.aa16.rows")
+    sc = H.golden_scene("horse_and_mug")
+    cam = sc.camera(0, m["width"], m["height"])
+    rt = tracer("horse_and_mug")
+    img = rt.render(cam, m["aa"])
+    st = rt.last_stats
+    rays = m["rays"]
+    print("8K 16x:", st.primary_rays, st.reflection_rays, st.shadow_rays, f"{st.ms_render:.1f} ms render, {st.ms_d2h:.2f} ms D2H,",
+          f"{st.total_rays / st.ms_render / 1e3:.0f} Mrays/s")
+    assert st.primary_rays == rays["primary"] == 7680 * 3840 * 256
+    assert abs(st.reflection_rays - rays["reflection"]) <= 1e-6 * rays["reflection"]
+    assert abs(st.shadow_rays - rays["shadow"]) <= 1e-6 * rays["shadow"]
+    got = img[m["rows"]]
+    rep = H.diff_report(gold, got)
+    print("golden rows:", rep)
+    assert H.within_tolerance(rep)
+    # the whole frame against the committed full-size golden (oracle frame whose PPM md5 equals the reference's)
+    full, fm = H.golden_image("horse_and_mug_8k.aa16.full")
+    frep = H.diff_report(full, img)
+    print("full frame vs reference:", frep)
+    assert H.within_tolerance(frep)
+    assert frep["max"] <= 1  # a culled-hit deviation moves one of 256 sub-samples: never more than 1/255 of a pixel
+    p = str(tmp_path / "h8k.ppm")
+    H.write_ppm(p, img)
+    h = hashlib.md5()
+    with open(p, "rb") as f:
+        for chunk in iter(lambda: f.read(1 << 24), b""):
+            h.update(chunk)
+    identical = h.hexdigest() == fm["ppm_md5"]
+    print("full-frame PPM md5", h.hexdigest(), "== reference's" if identical else "!= reference's " + fm["ppm_md5"])
+    assert identical == (frep["equal"] == frep["pixels"])
+    img2 = rt.render(cam, m["aa"])
+    assert np.array_equal(img, img2)
