@@ -104,7 +104,9 @@ typedef struct RtCamera {
 typedef struct RtBuildOptions {
   int32_t builder;    /* RT_BUILD_* */
   int32_t brute_force; /* 1: ignore the BVH and test every primitive (parity debugging) */
-  int32_t reserved[6];
+  int32_t no_exact_culling; /* 1: skip the reference-visibility check (a hit the reference's own box test would
+                               have culled is then reported; a few rays per 10^8 on the shipped scenes) */
+  int32_t reserved[5];
 } RtBuildOptions;
 
 /* counters are exact (device atomics); "ray" = one closest-hit query
@@ -114,6 +116,8 @@ typedef struct RtStats {
   uint64_t reflection_rays; /* reflection rays actually traced */
   uint64_t shadow_rays;
   uint64_t shadow_occluded;
+  uint64_t replayed_closest; /* closest-hit rays recomputed by the exact replay of the reference's traversal */
+  uint64_t replayed_any;     /* shadow rays recomputed likewise */
   float ms_render; /* device time of the render kernel(s), CUDA events */
   float ms_d2h;    /* device-to-host copy of the RGB8 frame */
   float ms_total;  /* camera known -> RGB8 on host */

@@ -297,6 +297,7 @@ typedef struct {
     V3 normal;
     int material_id;
     int exists;
+    int prim; /* debugging only: triangle index, or n_tris + sphere index */
 } Hit;
 
 /* raytracer.cpp:15-19 */
@@ -367,6 +368,12 @@ static Hit hit_triangle(const OrScene *s, const Ray *ray, const OTri *tr) {
     return p;
 }
 
+/* Debug switch (tests only): 1 makes every box test pass, i.e. every primitive is tested in the reference's
+ * visit order — the "no culling" variant of SURVEY.md 7.3 used to locate rays whose hit the reference's own
+ * slab test culls. */
+static volatile int g_no_culling = 0;
+void or_set_no_culling(int on) { g_no_culling = on; }
+
 /* raytracer.cpp:177-225 */
 static Hit first_hit(const OrScene *s, const Ray *ray, OrStats *st) {
     Hit best = {-1, {-1, -1, 0}, -1, 0};
@@ -379,6 +386,7 @@ static Hit first_hit(const OrScene *s, const Ray *ray, OrStats *st) {
         float tb;
         st->box_tests++;
         int ok = hit_box(ray, &nd->box, &tb);
+        if (g_no_culling) { ok = 1; tb = -FLT_MAX; }
         if (ok && tb <= tMax) {
             if (!nd->is_leaf) {
                 if (vget(ray->d, nd->axis) > 0) { stack[sp++] = nd->right; stack[sp++] = n + 1; }
@@ -387,11 +395,13 @@ static Hit first_hit(const OrScene *s, const Ray *ray, OrStats *st) {
                 for (int i = 0; i < nd->tri_count; i++) {
                     st->tri_tests++;
                     Hit h = hit_triangle(s, ray, &s->tris[s->leaf_tris[nd->tri_begin + i]]);
+                    h.prim = s->leaf_tris[nd->tri_begin + i];
                     if (h.exists && (h.tSmall < best.tSmall || best.tSmall == -1)) { best = h; tMax = best.tSmall; }
                 }
                 for (int i = 0; i < nd->sph_count; i++) {
                     st->sphere_tests++;
                     Hit h = hit_sphere(s, ray, &s->d.spheres[s->leaf_sphs[nd->sph_begin + i]]);
+                    h.prim = s->n_tris + s->leaf_sphs[nd->sph_begin + i];
                     if (h.exists && (h.tSmall < best.tSmall || best.tSmall == -1)) { best = h; tMax = best.tSmall; }
                 }
             }
@@ -409,7 +419,7 @@ static int any_hit_until(const OrScene *s, const Ray *ray, float t, OrStats *st)
         const ONode *nd = &s->nodes[n];
         float tb;
         st->box_tests++;
-        if (!hit_box(ray, &nd->box, &tb)) continue;
+        if (!hit_box(ray, &nd->box, &tb) && !g_no_culling) continue;
         if (!nd->is_leaf) {
             if (vget(ray->d, nd->axis) > 0) { stack[sp++] = nd->right; stack[sp++] = n + 1; }
             else { stack[sp++] = n + 1; stack[sp++] = nd->right; }
@@ -621,3 +631,52 @@ int or_specular_gate(float cosTheta) {
     float theta = (float) (acos((double) cosTheta) * 180 / 3.1415);
     return theta <= 90.01;
 }
+
+/* a block of sub-samples (debugging aid for tests: single thread, works with or_set_no_culling) */
+int or_render_block(const OrScene *s, const RtCamera *cam, int aa, long long row0, long long col0, int n_rows, int n_cols,
+                    unsigned char *out, OrStats *stats) {
+    if (!s || !cam || aa < 1 || !out) return -1;
+    EyeGen g = eye_init(cam, cam->image_width * aa, cam->image_height * aa);
+    OrStats st; memset(&st, 0, sizeof st);
+    for (int r = 0; r < n_rows; r++)
+        for (int c = 0; c < n_cols; c++) {
+            Ray ray = eye_ray(&g, row0 + r, col0 + c);
+            V3 col = ray_trace(s, &ray, 0, &st);
+            to_pixel(col, out + ((size_t) r * n_cols + c) * 3);
+        }
+    if (stats) *stats = st;
+    return 0;
+}
+
+/* debugging aid: the closest hit of an arbitrary ray; out8 = exists, prim, t, then the slab test of every node on
+ * the path from the root to that primitive's leaf is printed to stderr when verbose */
+int or_debug_first_hit(const OrScene *s, const float *o3, const float *d3, float *t_out, int *prim_out) {
+    Ray r = make_ray(v3(o3[0], o3[1], o3[2]), v3(d3[0], d3[1], d3[2]));
+    OrStats st; memset(&st, 0, sizeof st);
+    Hit h = first_hit(s, &r, &st);
+    *t_out = h.tSmall;
+    *prim_out = h.exists ? h.prim : -1;
+    return h.exists;
+}
+/* eye ray of a sub-sample: o3, d3 */
+void or_debug_eye_ray(const RtCamera *cam, int aa, long long row, long long col, float *o3, float *d3) {
+    EyeGen g = eye_init(cam, cam->image_width * aa, cam->image_height * aa);
+    Ray r = eye_ray(&g, row, col);
+    o3[0] = r.o.x; o3[1] = r.o.y; o3[2] = r.o.z; d3[0] = r.d.x; d3[1] = r.d.y; d3[2] = r.d.z;
+}
+/* slab test (raytracer.cpp:101-126) of node i for a ray: returns exists, *t = entry; box6 receives the box */
+int or_debug_node_box(const OrScene *s, int node, const float *o3, const float *d3, float *t, float *box6, int *meta4) {
+    Ray r = make_ray(v3(o3[0], o3[1], o3[2]), v3(d3[0], d3[1], d3[2]));
+    const ONode *nd = &s->nodes[node];
+    box6[0] = nd->box.min.x; box6[1] = nd->box.min.y; box6[2] = nd->box.min.z;
+    box6[3] = nd->box.max.x; box6[4] = nd->box.max.y; box6[5] = nd->box.max.z;
+    meta4[0] = nd->is_leaf; meta4[1] = nd->axis; meta4[2] = nd->right; meta4[3] = nd->tri_count + nd->sph_count;
+    return hit_box(&r, &nd->box, t);
+}
+int or_debug_leaf_has(const OrScene *s, int node, int prim) {
+    const ONode *nd = &s->nodes[node];
+    for (int i = 0; i < nd->tri_count; i++) if (s->leaf_tris[nd->tri_begin + i] == prim) return 1;
+    for (int i = 0; i < nd->sph_count; i++) if (s->n_tris + s->leaf_sphs[nd->sph_begin + i] == prim) return 1;
+    return 0;
+}
+int or_num_nodes(const OrScene *s) { return s->n_nodes; }

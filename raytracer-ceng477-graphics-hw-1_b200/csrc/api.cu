@@ -43,6 +43,8 @@ struct RtScene {
            *d_lights = nullptr;
     int *d_sph_mat = nullptr;
     uint32_t *d_ranks = nullptr;
+    float4 *d_ref_nodes = nullptr, *d_prim_bounds = nullptr;
+    int *d_ref_leaf_prims = nullptr, *d_slot_of_prim = nullptr;
     unsigned int *d_counter = nullptr;
     unsigned long long *d_stats = nullptr;
     unsigned char *d_frame = nullptr;  // grows on demand
@@ -229,7 +231,7 @@ int enqueue_part(RtScene *s, const RtCamera *cam, int aa, int rank, int world, u
     p.work_counter = s->d_counter;
     p.stats = s->d_stats;
     CU(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned int), stream));
-    CU(cudaMemsetAsync(s->d_stats, 0, 4 * sizeof(unsigned long long), stream));
+    CU(cudaMemsetAsync(s->d_stats, 0, 6 * sizeof(unsigned long long), stream));
     if (n_items == 0) return RT_OK;
     cudaError_t e;
     if (s->kernel == 2) {
@@ -253,12 +255,14 @@ int enqueue_part(RtScene *s, const RtCamera *cam, int aa, int rank, int world, u
 }
 
 int fetch_stats(RtScene *s, RtStats *stats) {
-    unsigned long long h[4];
+    unsigned long long h[6];
     CU(cudaMemcpy(h, s->d_stats, sizeof h, cudaMemcpyDeviceToHost));
     stats->primary_rays = h[0];
     stats->reflection_rays = h[1];
     stats->shadow_rays = h[2];
     stats->shadow_occluded = h[3];
+    stats->replayed_closest = h[4];
+    stats->replayed_any = h[5];
     return RT_OK;
 }
 
@@ -374,7 +378,8 @@ int rt_scene_create(const RtSceneDesc *desc, const RtBuildOptions *opts, RtScene
     // reference-order tie ranks
     std::vector<uint32_t> ranks;
     RefTreeStats rstats;
-    build_reference_ranks(*desc, ranks, rstats);
+    RefTree rtree;
+    build_reference_ranks(*desc, ranks, rstats, &rtree);
     std::vector<Aabb> bounds;
     primitive_bounds(*desc, bounds);
 
@@ -429,6 +434,20 @@ int rt_scene_create(const RtSceneDesc *desc, const RtBuildOptions *opts, RtScene
             prims[3 * (size_t) sidx + 2] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
+    std::vector<float4> prim_bounds((size_t) np * 2);
+    for (int i = 0; i < np; i++) {
+        prim_bounds[2 * (size_t) i] = make_float4(bounds[i].mn[0], bounds[i].mn[1], bounds[i].mn[2], 0.f);
+        prim_bounds[2 * (size_t) i + 1] = make_float4(bounds[i].mx[0], bounds[i].mx[1], bounds[i].mx[2], 0.f);
+    }
+    std::vector<int> slot_of_prim((size_t) np);
+    for (int sidx = 0; sidx < np; sidx++) slot_of_prim[bvh.prim_order[sidx]] = sidx;
+    std::vector<float4> ref_nodes(rtree.nodes.size() * 3);
+    for (size_t i = 0; i < rtree.nodes.size(); i++) {
+        const RefTreeNode &n = rtree.nodes[i];
+        ref_nodes[3 * i + 0] = make_float4(n.mn[0], n.mn[1], n.mn[2], bits(n.axis | (n.is_leaf ? 4 : 0)));
+        ref_nodes[3 * i + 1] = make_float4(n.mx[0], n.mx[1], n.mx[2], bits(n.right));
+        ref_nodes[3 * i + 2] = make_float4(bits(n.first), bits(n.count), 0.f, 0.f);
+    }
     std::vector<float4> tri_nm((size_t) nt), tri_nn((size_t) nt);
     for (int i = 0; i < nt; i++) {
         const RtTriangle &t = desc->triangles[i];
@@ -481,10 +500,14 @@ int rt_scene_create(const RtSceneDesc *desc, const RtBuildOptions *opts, RtScene
     if (rc == RT_OK) rc = upload(&s->d_sph_cr, sph_cr.data(), sph_cr.size());
     if (rc == RT_OK) rc = upload(&s->d_sph_mat, sph_mat.data(), sph_mat.size());
     if (rc == RT_OK) rc = upload(&s->d_ranks, ranks.data(), ranks.size());
+    if (rc == RT_OK) rc = upload(&s->d_ref_nodes, ref_nodes.data(), ref_nodes.size());
+    if (rc == RT_OK) rc = upload(&s->d_ref_leaf_prims, rtree.leaf_prims.data(), rtree.leaf_prims.size());
+    if (rc == RT_OK) rc = upload(&s->d_prim_bounds, prim_bounds.data(), prim_bounds.size());
+    if (rc == RT_OK) rc = upload(&s->d_slot_of_prim, slot_of_prim.data(), slot_of_prim.size());
     if (rc == RT_OK) rc = upload(&s->d_materials, mats.data(), mats.size());
     if (rc == RT_OK) rc = upload(&s->d_lights, lights.data(), lights.size());
     if (rc == RT_OK && cudaMalloc((void **) &s->d_counter, sizeof(unsigned int)) != cudaSuccess) rc = fail(RT_ERR_CUDA, "cudaMalloc");
-    if (rc == RT_OK && cudaMalloc((void **) &s->d_stats, 4 * sizeof(unsigned long long)) != cudaSuccess) rc = fail(RT_ERR_CUDA, "cudaMalloc");
+    if (rc == RT_OK && cudaMalloc((void **) &s->d_stats, 6 * sizeof(unsigned long long)) != cudaSuccess) rc = fail(RT_ERR_CUDA, "cudaMalloc");
     if (rc == RT_OK && cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) rc = fail(RT_ERR_CUDA, "cudaStreamCreate");
     for (int i = 0; i < 4 && rc == RT_OK; i++)
         if (cudaEventCreate(&s->ev[i]) != cudaSuccess) rc = fail(RT_ERR_CUDA, "cudaEventCreate");
@@ -517,6 +540,11 @@ int rt_scene_create(const RtSceneDesc *desc, const RtBuildOptions *opts, RtScene
     b.sph_cr = s->d_sph_cr;
     b.sph_mat = s->d_sph_mat;
     b.ranks = s->d_ranks;
+    b.ref_nodes = s->d_ref_nodes;
+    b.ref_leaf_prims = s->d_ref_leaf_prims;
+    b.prim_bounds = s->d_prim_bounds;
+    b.slot_of_prim = s->d_slot_of_prim;
+    b.exact_culling = (opts && opts->no_exact_culling) ? 0 : 1;
     b.materials = s->d_materials;
     b.lights = s->d_lights;
     b.n_nodes = (int) bvh.nodes.size();
@@ -559,6 +587,10 @@ void rt_scene_destroy(RtScene *s) {
     cudaFree(s->d_sph_cr);
     cudaFree(s->d_sph_mat);
     cudaFree(s->d_ranks);
+    cudaFree(s->d_ref_nodes);
+    cudaFree(s->d_ref_leaf_prims);
+    cudaFree(s->d_prim_bounds);
+    cudaFree(s->d_slot_of_prim);
     cudaFree(s->d_materials);
     cudaFree(s->d_lights);
     cudaFree(s->d_counter);
@@ -731,6 +763,8 @@ int rt_render_multi(RtScene *const *scenes, int n, const RtCamera *cam, int aa, 
             stats->reflection_rays += part.reflection_rays;
             stats->shadow_rays += part.shadow_rays;
             stats->shadow_occluded += part.shadow_occluded;
+            stats->replayed_closest += part.replayed_closest;
+            stats->replayed_any += part.replayed_any;
         }
         CU(cudaSetDevice(root->device));
         cudaEventElapsedTime(&stats->ms_render, root->ev[0], root->ev[1]);

@@ -53,6 +53,7 @@ struct RefNode {
     int axis;
     int left, right;   // -1 for leaves
     int first, count;  // leaf range in the ordered id array
+    float mn[3], mx[3];
 };
 
 struct RefBuilder {
@@ -67,7 +68,7 @@ struct RefBuilder {
 
     int build(int lo, int hi, int depth) {
         const int me = (int) nodes.size();
-        nodes.push_back(RefNode{0, -1, -1, lo, hi - lo});
+        nodes.push_back(RefNode{0, -1, -1, lo, hi - lo, {0, 0, 0}, {0, 0, 0}});
         stats.nodes++;
         if (depth > stats.max_depth) stats.max_depth = depth;
         float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
@@ -78,6 +79,7 @@ struct RefBuilder {
                 if (b.mx[a] > mx[a]) mx[a] = b.mx[a];
             }
         }
+        for (int a = 0; a < 3; a++) nodes[me].mn[a] = mn[a], nodes[me].mx[a] = mx[a];
         bool split = false;
         int n_left = 0;
         if (hi - lo > 1 && depth < 19) {            // bvh.h:57, MAX_DEPTH bvh.h:18
@@ -125,7 +127,7 @@ struct RefBuilder {
 
 }  // namespace
 
-void build_reference_ranks(const RtSceneDesc &d, std::vector<uint32_t> &ranks, RefTreeStats &stats) {
+void build_reference_ranks(const RtSceneDesc &d, std::vector<uint32_t> &ranks, RefTreeStats &stats, RefTree *tree) {
     std::vector<Aabb> bounds;
     primitive_bounds(d, bounds);
     RefBuilder b(bounds);
@@ -153,6 +155,25 @@ void build_reference_ranks(const RtSceneDesc &d, std::vector<uint32_t> &ranks, R
     for (int i = 0; i < np; i++) b.ids[i] = i;  // triangles first, then spheres: leaf order of raytracer.cpp:199-216
     b.build(0, np, 0);
     stats = b.stats;
+
+    if (tree) {  // the reference's flattened tree itself (bvh.h:81-105 order: left child = index + 1)
+        const int nn = (int) b.nodes.size();
+        tree->nodes.resize((size_t) nn);
+        tree->leaf_prims = b.ids;
+        tree->leaf_of_prim.assign((size_t) np, 0);
+        for (int i = 0; i < nn; i++) {
+            const RefNode &n = b.nodes[i];
+            RefTreeNode &o = tree->nodes[i];
+            for (int a = 0; a < 3; a++) o.mn[a] = n.mn[a], o.mx[a] = n.mx[a];
+            o.axis = n.axis;
+            o.is_leaf = n.left < 0;
+            o.right = n.right;
+            o.first = n.first;
+            o.count = n.count;
+            if (n.left < 0)
+                for (int k = 0; k < n.count; k++) tree->leaf_of_prim[b.ids[n.first + k]] = i;
+        }
+    }
 
     std::vector<int> stack;
     for (int oct = 0; oct < 8; oct++) {

@@ -22,9 +22,10 @@ namespace rtb {
 // Closest hit: argmin over all reported intersections of (t, reference visit rank).
 // ANY: true as soon as some primitive reports t < limit (raytracer.cpp:237, 245).
 template <bool ANY>
-RT_DEV bool traverse(const RenderParams &p, const Ray &r, float limit, float &tbest, int &pbest) {
+RT_DEV bool traverse(const RenderParams &p, const Ray &r, float limit, float &tbest, int &pbest, float &tsecond) {
     tbest = limit;
     pbest = -1;
+    tsecond = FLT_MAX;
     if (p.n_nodes == 0) return false;
 
     if (p.brute_force) {
@@ -33,11 +34,13 @@ RT_DEV bool traverse(const RenderParams &p, const Ray &r, float limit, float &tb
             int prim;
             if (hit_prim(p, r, s, t, prim)) {
                 if (ANY) {
-                    if (t < limit) return true;
-                } else if (pbest < 0 || t < tbest ||
-                           (t == tbest && __ldg(&p.ranks[r.oct * p.n_prims + prim]) < __ldg(&p.ranks[r.oct * p.n_prims + pbest]))) {
-                    tbest = t;
-                    pbest = prim;
+                    if (t < limit) {
+                        tbest = t;
+                        pbest = prim;
+                        return true;
+                    }
+                } else {
+                    closest_update(p, r.oct, t, prim, tbest, pbest, tsecond);
                 }
             }
         }
@@ -81,11 +84,13 @@ RT_DEV bool traverse(const RenderParams &p, const Ray &r, float limit, float &tb
                 int prim;
                 if (hit_prim(p, r, s, t, prim)) {
                     if (ANY) {
-                        if (t < limit) return true;
-                    } else if (pbest < 0 || t < tbest ||
-                               (t == tbest && __ldg(&p.ranks[r.oct * p.n_prims + prim]) < __ldg(&p.ranks[r.oct * p.n_prims + pbest]))) {
-                        tbest = t;
-                        pbest = prim;
+                        if (t < limit) {
+                            tbest = t;
+                            pbest = prim;
+                            return true;
+                        }
+                    } else {
+                        closest_update(p, r.oct, t, prim, tbest, pbest, tsecond);
                     }
                 }
             }
@@ -115,7 +120,14 @@ RT_DEV V3 trace_path(const RenderParams &p, V3 o, V3 d, Counters &cnt) {
         const Ray ray = make_ray(o, d);
         float t;
         int prim;
-        if (!traverse<false>(p, ray, FLT_MAX, t, prim)) {  // raytracer.cpp:442-449
+        float t2;
+        bool hit = traverse<false>(p, ray, FLT_MAX, t, prim, t2);
+        if (hit && p.exact_culling && !robust_visible(p, ray, prim, t, t2)) {  // doubtful: replay the reference's traversal
+            cnt.replay_closest++;
+            ref_closest(p, ray, t, prim);
+            hit = prim >= 0;
+        }
+        if (!hit) {  // raytracer.cpp:442-449
             result = depth > 0 ? mk(0.0f, 0.0f, 0.0f) : ld3(p.background);
             break;
         }
@@ -149,7 +161,13 @@ RT_DEV V3 trace_path(const RenderParams &p, V3 o, V3 d, Counters &cnt) {
             const Ray sray = make_ray(Pe, wi);
             float ts;
             int ps;
-            if (traverse<true>(p, sray, dist, ts, ps)) {
+            float ts2;
+            bool occluded = traverse<true>(p, sray, dist, ts, ps, ts2);
+            if (occluded && p.exact_culling && !robust_visible(p, sray, ps, ts, FLT_MAX)) {
+                cnt.replay_any++;
+                occluded = ref_any(p, sray, dist);
+            }
+            if (occluded) {
                 cnt.occluded++;
                 continue;
             }
@@ -205,7 +223,7 @@ __global__ void __launch_bounds__(kThreads, RT_MIN_CTAS) render_kernel(const __g
     const int n_slots = Sw * Sh;
     const int items_per_tile = p.items_x * p.items_x;
     const bool warp_in_one_pixel = (f % 8) == 0;
-    Counters cnt = {0u, 0u, 0u, 0u};
+    Counters cnt = {0u, 0u, 0u, 0u, 0u, 0u};
     const V3 E0 = ld3(p.e), Q = ld3(p.q), U = ld3(p.u), Vv = ld3(p.v);
 
     for (;;) {
@@ -293,11 +311,15 @@ __global__ void __launch_bounds__(kThreads, RT_MIN_CTAS) render_kernel(const __g
     unsigned v1 = __reduce_add_sync(0xffffffffu, cnt.reflection);
     unsigned v2 = __reduce_add_sync(0xffffffffu, cnt.shadow);
     unsigned v3 = __reduce_add_sync(0xffffffffu, cnt.occluded);
+    unsigned v4 = __reduce_add_sync(0xffffffffu, cnt.replay_closest);
+    unsigned v5 = __reduce_add_sync(0xffffffffu, cnt.replay_any);
     if ((tid & 31) == 0) {
         atomicAdd(&p.stats[0], (unsigned long long) v0);
         atomicAdd(&p.stats[1], (unsigned long long) v1);
         atomicAdd(&p.stats[2], (unsigned long long) v2);
         atomicAdd(&p.stats[3], (unsigned long long) v3);
+        atomicAdd(&p.stats[4], (unsigned long long) v4);
+        atomicAdd(&p.stats[5], (unsigned long long) v5);
     }
 }
 
@@ -319,7 +341,7 @@ __global__ void __launch_bounds__(kThreads3, RT_MIN_CTAS3) render_kernel_v3(cons
     const int f = p.f, P = p.P;
     const int items_per_tile = p.items_x * p.items_x;
     const bool warp_in_one_pixel = (f % 8) == 0;
-    Counters cnt = {0u, 0u, 0u, 0u};
+    Counters cnt = {0u, 0u, 0u, 0u, 0u, 0u};
     const V3 E0 = ld3(p.e), Q = ld3(p.q), U = ld3(p.u), Vv = ld3(p.v);
 
     for (;;) {
@@ -404,11 +426,15 @@ __global__ void __launch_bounds__(kThreads3, RT_MIN_CTAS3) render_kernel_v3(cons
     unsigned v1 = __reduce_add_sync(0xffffffffu, cnt.reflection);
     unsigned v2 = __reduce_add_sync(0xffffffffu, cnt.shadow);
     unsigned v3 = __reduce_add_sync(0xffffffffu, cnt.occluded);
+    unsigned v4 = __reduce_add_sync(0xffffffffu, cnt.replay_closest);
+    unsigned v5 = __reduce_add_sync(0xffffffffu, cnt.replay_any);
     if (lane == 0) {
         atomicAdd(&p.stats[0], (unsigned long long) v0);
         atomicAdd(&p.stats[1], (unsigned long long) v1);
         atomicAdd(&p.stats[2], (unsigned long long) v2);
         atomicAdd(&p.stats[3], (unsigned long long) v3);
+        atomicAdd(&p.stats[4], (unsigned long long) v4);
+        atomicAdd(&p.stats[5], (unsigned long long) v5);
     }
 }
 

@@ -21,6 +21,11 @@ struct RenderParams {
     const float4 *sph_cr;
     const int *sph_mat;
     const uint32_t *ranks;
+    const float4 *ref_nodes;        // reference tree (exact culling replay)
+    const int *ref_leaf_prims;
+    const float4 *prim_bounds;      // [2 * n_prims] un-padded bounds of each primitive as the reference computes them
+    const int *slot_of_prim;        // prim id -> slot in `prims`
+    int exact_culling;              // 1: reproduce the reference's box-culling decisions (default)
     const float4 *materials;
     const float4 *lights;
     int n_nodes, n_tris, n_prims, n_lights;
@@ -44,7 +49,7 @@ struct RenderParams {
     int refill_threshold;  // kernel 2: refill idle lanes once <= this many lanes are busy
     unsigned char *out;
     unsigned int *work_counter;      // zeroed before launch
-    unsigned long long *stats;       // [4] primary, reflection, shadow, occluded
+    unsigned long long *stats;       // [6] primary, reflection, shadow, occluded, replayed closest, replayed any
 };
 
 }  // namespace rtb

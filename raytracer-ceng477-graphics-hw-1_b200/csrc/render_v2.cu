@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
     const int items_per_tile = p.items_x * p.items_x;
     const V3 E0 = ld3(p.e), Q = ld3(p.q), U = ld3(p.u), Vv = ld3(p.v);
     const V3 Ia = ld3(p.ambient);
-    Counters cnt = {0u, 0u, 0u, 0u};
+    Counters cnt = {0u, 0u, 0u, 0u, 0u, 0u};
 
     // reflection levels of the lane's current path (folded back to front at the end of the path)
     V3 local_stack[kMaxSupportedDepth + 1];
@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
             const bool any = phase == kShadow;
             float tbest = limit;
             int pbest = -1;
+            float tsecond = FLT_MAX;
             bool occluded = false;
             if (phase != kIdle && p.n_nodes > 0) {
                 if (p.brute_force) {
@@ -131,11 +132,13 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
                         int prim;
                         if (hit_prim(p, ray, s, t, prim)) {
                             if (any) {
-                                if (t < limit) occluded = true;
-                            } else if (pbest < 0 || t < tbest ||
-                                       (t == tbest && __ldg(&p.ranks[ray.oct * p.n_prims + prim]) < __ldg(&p.ranks[ray.oct * p.n_prims + pbest]))) {
-                                tbest = t;
-                                pbest = prim;
+                                if (t < limit) {
+                                    occluded = true;
+                                    tbest = t;
+                                    pbest = prim;
+                                }
+                            } else {
+                                closest_update(p, ray.oct, t, prim, tbest, pbest, tsecond);
                             }
                         }
                     }
@@ -177,18 +180,29 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
                                     if (any) {
                                         if (t < limit) {  // raytracer.cpp:237, 245
                                             occluded = true;
+                                            tbest = t;
+                                            pbest = prim;
                                             node = kSentinel;
                                             break;
                                         }
-                                    } else if (pbest < 0 || t < tbest ||
-                                               (t == tbest && __ldg(&p.ranks[ray.oct * p.n_prims + prim]) < __ldg(&p.ranks[ray.oct * p.n_prims + pbest]))) {
-                                        tbest = t;
-                                        pbest = prim;
+                                    } else {
+                                        closest_update(p, ray.oct, t, prim, tbest, pbest, tsecond);
                                     }
                                 }
                             }
                         }
                     }
+                }
+            }
+
+            // reference visibility: a doubtful hit is replayed on the reference's own tree (device_common.cuh)
+            if (p.exact_culling && phase != kIdle && pbest >= 0 && !robust_visible(p, ray, pbest, tbest, any ? FLT_MAX : tsecond)) {
+                if (any) {
+                    cnt.replay_any++;
+                    occluded = ref_any(p, ray, limit);
+                } else {
+                    cnt.replay_closest++;
+                    ref_closest(p, ray, tbest, pbest);
                 }
             }
 
@@ -326,11 +340,15 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
     unsigned v1 = __reduce_add_sync(0xffffffffu, cnt.reflection);
     unsigned v2 = __reduce_add_sync(0xffffffffu, cnt.shadow);
     unsigned v3 = __reduce_add_sync(0xffffffffu, cnt.occluded);
+    unsigned v4 = __reduce_add_sync(0xffffffffu, cnt.replay_closest);
+    unsigned v5 = __reduce_add_sync(0xffffffffu, cnt.replay_any);
     if (lane == 0) {
         atomicAdd(&p.stats[0], (unsigned long long) v0);
         atomicAdd(&p.stats[1], (unsigned long long) v1);
         atomicAdd(&p.stats[2], (unsigned long long) v2);
         atomicAdd(&p.stats[3], (unsigned long long) v3);
+        atomicAdd(&p.stats[4], (unsigned long long) v4);
+        atomicAdd(&p.stats[5], (unsigned long long) v5);
     }
 }
 

@@ -31,6 +31,9 @@ namespace rtb {
 //  sph_cr     float4[ns]            centre + radius; sph_mat int[ns]
 //  ranks      uint32[8 * n_prims]   visit rank of prim_id in the reference's traversal order for each
 //                                   ray-direction sign octant (bit a <=> dir[a] > 0) — exact-t tie breaking
+//  ref_nodes  float4[3 * n_ref]     the reference's own tree: [0] = min.xyz bits(axis | is_leaf << 2)
+//                                   [1] = max.xyz bits(right child)  [2] = bits(first) bits(count) - -   (left child = index + 1)
+//  ref_leaf_prims int[n_prims]      prim ids in the reference's leaf order; slot_of_prim int[n_prims]; prim_bounds float4[2 * n_prims]
 //  materials  float4[4 * nm]        [0] = ka.xyz phong  [1] = kd.xyz bits(is_mirror)  [2] = ks.xyz 0  [3] = km.xyz 0
 //  lights     float4[2 * nl]        [0] = position.xyz  [1] = intensity.xyz
 // ---------------------------------------------------------------------------------------------
@@ -65,7 +68,20 @@ void primitive_bounds(const RtSceneDesc &d, std::vector<Aabb> &out);
 struct RefTreeStats {
     int nodes = 0, leaves = 0, max_leaf = 0, max_depth = 0;
 };
-void build_reference_ranks(const RtSceneDesc &d, std::vector<uint32_t> &ranks /* [8][np] */, RefTreeStats &stats);
+// The reference's flattened tree (pre-order, left child = index + 1, bvh.h:81-105) with its un-padded boxes:
+// used on the device to decide whether the reference's own box culling would have reached a hit
+// (DESIGN.md "reference visibility") and, for the doubtful few rays, to replay its traversal exactly.
+struct RefTreeNode {
+    float mn[3], mx[3];
+    int axis, is_leaf, right, first, count;
+};
+struct RefTree {
+    std::vector<RefTreeNode> nodes;
+    std::vector<int> leaf_prims;    // prim ids in the reference's leaf order (triangles before spheres inside a leaf)
+    std::vector<int> leaf_of_prim;  // node index of the leaf holding each primitive
+};
+void build_reference_ranks(const RtSceneDesc &d, std::vector<uint32_t> &ranks /* [8][np] */, RefTreeStats &stats,
+                           RefTree *tree = nullptr);
 
 // Host binned-SAH BVH2 (quality yardstick and fallback for tiny scenes).
 void build_bvh_sah_host(const std::vector<Aabb> &bounds, HostBvh &out);

@@ -63,12 +63,14 @@ class RtCamera(C.Structure):
 
 
 class RtBuildOptions(C.Structure):
-    _fields_ = [("builder", C.c_int32), ("brute_force", C.c_int32), ("reserved", C.c_int32 * 6)]
+    _fields_ = [("builder", C.c_int32), ("brute_force", C.c_int32), ("no_exact_culling", C.c_int32),
+                ("reserved", C.c_int32 * 5)]
 
 
 class RtStats(C.Structure):
     _fields_ = [("primary_rays", C.c_uint64), ("reflection_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
-                ("shadow_occluded", C.c_uint64), ("ms_render", C.c_float), ("ms_d2h", C.c_float),
+                ("shadow_occluded", C.c_uint64), ("replayed_closest", C.c_uint64), ("replayed_any", C.c_uint64),
+                ("ms_render", C.c_float), ("ms_d2h", C.c_float),
                 ("ms_total", C.c_float), ("n_launches", C.c_int32), ("reserved", C.c_int32 * 3)]
 
     @property
@@ -261,10 +263,10 @@ def _check(rc):
 class RayTracer:
     """RayTracer(scene) / render(camera) — raytracer.cpp:335, :362 — on the current CUDA device."""
 
-    def __init__(self, scene, builder=RT_BUILD_DEFAULT, brute_force=False):
+    def __init__(self, scene, builder=RT_BUILD_DEFAULT, brute_force=False, exact_culling=True):
         self.L = cuda_lib()
         self.scene = scene
-        opts = RtBuildOptions(builder, 1 if brute_force else 0)
+        opts = RtBuildOptions(builder, 1 if brute_force else 0, 0 if exact_culling else 1)
         h = C.c_void_p()
         _check(self.L.rt_scene_create(C.byref(scene.desc), C.byref(opts), C.byref(h)))
         self.h = h
