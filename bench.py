@@ -43,6 +43,9 @@ def parse_args():
     ap.add_argument("--builder", default="default", choices=["default", "sah", "lbvh"])
     ap.add_argument("--cpu-rows", type=int, default=0, help="sub-sample rows in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="nccl", choices=["nccl", "p2p"],
+                    help="N>1: nccl = packed tiles + one NCCL gather + scatter kernel; p2p = every rank's kernel stores its "
+                         "pixels straight into rank 0's frame over NVLink (CUDA IPC peer mapping), then one barrier")
     return ap.parse_args()
 
 
@@ -212,10 +215,19 @@ def run_b200(args):
     host_frame = torch.empty(frame_bytes, dtype=torch.uint8, pin_memory=True) if rank == 0 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
+    peer = None
+    if world > 1 and args.gather == "p2p":
+        peer = H.rt_b200.PeerFrame(dist, rank, frame_bytes)
+        if rank == 0:
+            frame = peer.as_tensor()
+
     def device_step():
         """render my tiles -> (gather -> assemble on rank 0); everything on torch's current stream"""
         if world == 1:
             rt.render_part_into_frame(cam, aa, 0, 1, frame.data_ptr(), stream.cuda_stream, want_stats=False)
+        elif peer is not None:
+            rt.render_part_into_frame(cam, aa, rank, world, peer.ptr.value, stream.cuda_stream, want_stats=False)
+            dist.barrier()  # stream-ordered: rank 0 may read the frame once every rank's kernel has retired
         else:
             rt.render_part(cam, aa, rank, world, my_tiles.data_ptr(), stream.cuda_stream, want_stats=False)
             H.rt_b200.gather_parts(dist, my_tiles, all_parts, rank)
@@ -256,6 +268,10 @@ def run_b200(args):
         if world == 1:
             rt.render_part_into_frame(cam, aa, 0, 1, frame.data_ptr(), stream.cuda_stream, want_stats=False)
             e1.record(stream)
+        elif peer is not None:
+            rt.render_part_into_frame(cam, aa, rank, world, peer.ptr.value, stream.cuda_stream, want_stats=False)
+            e1.record(stream)
+            dist.barrier()
         else:
             rt.render_part(cam, aa, rank, world, my_tiles.data_ptr(), stream.cuda_stream, want_stats=False)
             e1.record(stream)
@@ -333,7 +349,8 @@ def run_b200(args):
                 "data": "reference's shipped scene (tests/golden/scenes, deterministic; the metric is defined on it, not on synthetic data)",
                 "config": {"workload": workload_name(args), "rays_per_frame": rays, "primary": primary, "reflection": reflection,
                            "shadow": shadow, "shadow_occluded": occluded, "parallelism": f"tiles32x32_interleaved_x{world}",
-                           "gather": "none" if world == 1 else "nccl gather of packed tiles + scatter kernel",
+                           "gather": "none" if world == 1 else ("fused: kernels store into rank 0's frame over NVLink P2P (CUDA IPC), one barrier" if peer is not None
+                                                               else "nccl gather of packed tiles + scatter kernel"),
                            "l2": "flushed between timed iterations (256 MiB write)", "bvh": {0: "default", 1: "lbvh_gpu", 2: "sah_host"}[info.builder],
                            "bvh_nodes": info.bvh_nodes, "scene_build_s": build_s, "frame_sha256": frame_sha},
                 "ms_per_frame": ms_per_step, "render_kernel_ms": kernel_ms, "wall_s_timed_region": wall_s,
@@ -342,13 +359,16 @@ def run_b200(args):
                         "h2d_bytes_per_step": ctypes.sizeof(H.RtCamera) * world, "d2h_bytes_per_step": frame_bytes,
                         "api": "rt_render (C-ABI) via rt_b200.RayTracer.render into pinned host memory" if world == 1
                         else "rt_render_part + NCCL gather + rt_assemble_tiles + D2H into pinned host memory"},
-                "gpu_launches": args.steps * (world + (1 if world > 1 else 0)),
+                "gpu_launches": args.steps * (world + (1 if (world > 1 and peer is None) else 0)),
                 "roofline": roofline}
         if world == 1 and not args.no_cpu_baseline:
             base = reference_sample(args, 1, 0)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
     rt.close()
+    if peer is not None:
+        dist.barrier()
+        peer.close()
     if dist:
         dist.barrier()
         dist.destroy_process_group()

@@ -162,7 +162,10 @@ int rt_render(RtScene *scene, const RtCamera *cam, int aa_factor, unsigned char 
 /* ---- multi-GPU: interleaved tiles, scene replicated per GPU ---------------
  * The output image is cut into RT_TILE x RT_TILE pixel tiles, numbered
  * row-major; tile k belongs to part (k % part_world).  This mirrors the
- * reference's interleaved rows (raytracer.cpp:353) for load balance. */
+ * reference's interleaved rows (raytracer.cpp:353) for load balance.  When
+ * the number of tile columns is a multiple of part_world, the numbering uses
+ * one extra (empty) phantom column so that a part's tiles run diagonally
+ * instead of in fixed vertical stripes. */
 #define RT_TILE 32
 
 /* number of tiles part `part_rank` owns, and bytes of its packed tile buffer
@@ -194,6 +197,18 @@ int rt_assemble_tiles(const RtCamera *cam, int part_world, const void *d_parts,
  * peer copies, one D2H. */
 int rt_render_multi(RtScene *const *scenes, int n_gpus, const RtCamera *cam, int aa_factor,
                     unsigned char *rgb_out, RtStats *stats);
+
+/* ---- peer memory for the fused gather (rt_render_part_into_frame) ------------
+ * One process per GPU: the gathering rank allocates the frame with
+ * rt_device_alloc and exports it; every other rank maps it with rt_ipc_open
+ * (CUDA IPC, peer access over NVLink) and passes the mapped pointer as d_frame,
+ * so its render kernel stores finished pixels straight into GPU 0's memory. */
+#define RT_IPC_HANDLE_BYTES 64
+int rt_device_alloc(int64_t bytes, void **d_ptr);
+int rt_device_free(void *d_ptr);
+int rt_ipc_export(void *d_ptr, unsigned char handle[RT_IPC_HANDLE_BYTES]);
+int rt_ipc_open(const unsigned char handle[RT_IPC_HANDLE_BYTES], void **d_ptr);
+int rt_ipc_close(void *d_ptr);
 
 /* ---- host-only hooks: no CUDA call inside, usable on a machine without a GPU.
  * They expose the host-side logic of rt_scene_create to CPU tests. */

@@ -251,6 +251,11 @@ def cuda_lib():
                                        C.POINTER(RtStats)]
         L.rt_assemble_tiles.argtypes = [C.POINTER(RtCamera), C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.rt_render_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(RtCamera), C.c_int, C.c_void_p, C.POINTER(RtStats)]
+        L.rt_device_alloc.argtypes = [C.c_int64, C.POINTER(C.c_void_p)]
+        L.rt_device_free.argtypes = [C.c_void_p]
+        L.rt_ipc_export.argtypes = [C.c_void_p, C.c_char_p]
+        L.rt_ipc_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        L.rt_ipc_close.argtypes = [C.c_void_p]
         _cuda = L
     return _cuda
 
@@ -328,12 +333,16 @@ class RayTracer:
 # no other data-path communication) and scatters them into the row-major frame.
 
 
-def tile_grid(width, height):
-    return (width + RT_TILE - 1) // RT_TILE, (height + RT_TILE - 1) // RT_TILE
+def tile_grid(width, height, world=1):
+    """Tile columns (incl. the phantom column that rt_b200.h describes) and tile rows."""
+    tx, ty = (width + RT_TILE - 1) // RT_TILE, (height + RT_TILE - 1) // RT_TILE
+    if world > 1 and tx % world == 0:
+        tx += 1
+    return tx, ty
 
 
 def part_tile_ids(width, height, rank, world):
-    tx, ty = tile_grid(width, height)
+    tx, ty = tile_grid(width, height, world)
     return range(rank, tx * ty, world)
 
 
@@ -346,7 +355,7 @@ def gather_parts(dist, my_tiles, all_parts, rank, dst=0):
 def pack_tiles_host(frame, rank, world):
     """Host restatement of the packed layout rt_render_part writes (tests and debugging only)."""
     h, w, _ = frame.shape
-    tx, _ = tile_grid(w, h)
+    tx, _ = tile_grid(w, h, world)
     ids = part_tile_ids(w, h, rank, world)
     out = np.zeros((len(ids), RT_TILE, RT_TILE, 3), np.uint8)
     for i, k in enumerate(ids):
@@ -358,7 +367,7 @@ def pack_tiles_host(frame, rank, world):
 
 def assemble_tiles_host(parts, width, height, world):
     """Host restatement of rt_assemble_tiles: parts is [world, stride] uint8."""
-    tx, _ = tile_grid(width, height)
+    tx, _ = tile_grid(width, height, world)
     frame = np.zeros((height, width, 3), np.uint8)
     for r in range(world):
         ids = part_tile_ids(width, height, r, world)
@@ -366,5 +375,43 @@ def assemble_tiles_host(parts, width, height, world):
         for i, k in enumerate(ids):
             y0, x0 = (k // tx) * RT_TILE, (k % tx) * RT_TILE
             hh, ww = min(RT_TILE, height - y0), min(RT_TILE, width - x0)
-            frame[y0:y0 + hh, x0:x0 + ww] = tiles[i, :hh, :ww]
+            if ww > 0:
+                frame[y0:y0 + hh, x0:x0 + ww] = tiles[i, :hh, :ww]
     return frame
+
+
+class PeerFrame:
+    """The row-major RGB8 frame on the gathering GPU, mapped into every rank (CUDA IPC over NVLink) so that
+    rt_render_part_into_frame stores finished pixels straight into it: the gather is fused into the kernel."""
+
+    def __init__(self, dist, rank, nbytes, root=0):
+        self.L = cuda_lib()
+        self.rank, self.root, self.nbytes = rank, root, nbytes
+        self.ptr = C.c_void_p()
+        payload = [None]
+        if rank == root:
+            _check(self.L.rt_device_alloc(nbytes, C.byref(self.ptr)))
+            h = C.create_string_buffer(64)
+            _check(self.L.rt_ipc_export(self.ptr, h))
+            payload = [h.raw]
+        dist.broadcast_object_list(payload, src=root)
+        if rank != root:
+            _check(self.L.rt_ipc_open(payload[0], C.byref(self.ptr)))
+
+    def as_tensor(self):
+        """torch uint8 view of the frame (root only)."""
+        import torch
+
+        class _Ext:
+            pass
+        e = _Ext()
+        e.__cuda_array_interface__ = {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr.value, False), "version": 2}
+        return torch.as_tensor(e, device="cuda")
+
+    def close(self):
+        if self.ptr:
+            if self.rank == self.root:
+                self.L.rt_device_free(self.ptr)
+            else:
+                self.L.rt_ipc_close(self.ptr)
+            self.ptr = C.c_void_p()

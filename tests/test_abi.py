@@ -29,8 +29,10 @@ def test_tile_partition_arithmetic():
     cam = H.RtCamera()
     for (w, h) in [(1, 1), (32, 32), (33, 31), (250, 190), (1440, 720), (7680, 3840)]:
         cam.image_width, cam.image_height = w, h
-        tiles = ((w + 31) // 32) * ((h + 31) // 32)
         for world in (1, 2, 3, 4, 8):
+            tx, ty = H.rt_b200.tile_grid(w, h, world)  # includes the phantom column when tiles_x % world == 0
+            assert tx in ((w + 31) // 32, (w + 31) // 32 + 1) and (tx % world != 0 or world == 1)
+            tiles = tx * ty
             per = [L.rt_part_tiles(C.byref(cam), r, world) for r in range(world)]
             assert sum(per) == tiles
             assert per == [len(range(r, tiles, world)) for r in range(world)]

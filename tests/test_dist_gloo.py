@@ -45,7 +45,7 @@ def _worker(rank, world, port, w, h, aa, result_path):
         dist.all_reduce(cnt)
         if rank == 0:
             got = rt.assemble_tiles_host(all_parts.numpy(), w, h, world)
-            tx, ty = rt.tile_grid(w, h)
+            tx, ty = rt.tile_grid(w, h, world)
             ok = np.array_equal(got, full) and int(cnt.item()) == tx * ty
             open(result_path, "w").write("ok" if ok else "mismatch")
         dist.barrier()
