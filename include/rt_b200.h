@@ -97,9 +97,10 @@ typedef struct RtCamera {
 } RtCamera;
 
 /* acceleration-structure builders (rt_scene_create) */
-#define RT_BUILD_DEFAULT 0
+#define RT_BUILD_DEFAULT 0 /* = RT_BUILD_PLOC_GPU */
 #define RT_BUILD_LBVH_GPU 1 /* Morton + radix sort + Karras on the GPU */
 #define RT_BUILD_SAH_HOST 2 /* binned SAH on the host (quality yardstick) */
+#define RT_BUILD_PLOC_GPU 3 /* Morton sort + PLOC agglomerative clustering + SAH leaf collapse on the GPU */
 
 typedef struct RtBuildOptions {
   int32_t builder;    /* RT_BUILD_* */

@@ -303,6 +303,167 @@ __global__ void emit_kernel(const unsigned long long *keys, const Aabb *bounds, 
     out[i] = h;
 }
 
+// ---- PLOC: parallel locally-ordered clustering (Meister & Bittner 2018) on the Morton-sorted primitives --------
+// One CTA of 1024 threads (the shipped scenes have <= 32 K primitives; the build is a one-off per scene):
+// every round, each cluster looks `kPlocRadius` neighbours left and right in the current (Morton) order for the
+// partner whose merged box has the smallest area; mutual nearest neighbours merge into a new node; the cluster
+// list is compacted with a block-wide prefix sum.  SAH cost / leaf collapse are evaluated when a node is
+// created (children always exist already); DFS positions are then pushed down batch by batch so that every
+// subtree owns a contiguous range of the final primitive order.
+constexpr int kPlocRadius = 16;
+constexpr int kPlocThreads = 1024;
+
+struct PlocNode {
+    Aabb box;
+    int left, right;   // node ids; leaves are ids 0..n-1 (sorted position), internal ids n..2n-2
+    int size;          // primitives below
+    int first;         // DFS position of the leftmost primitive
+    float cost;
+    int collapsed;
+};
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int *smem, int &total) {
+    // smem: kPlocThreads ints
+    const int t = threadIdx.x;
+    smem[t] = v;
+    __syncthreads();
+    for (int off = 1; off < kPlocThreads; off <<= 1) {
+        int add = (t >= off) ? smem[t - off] : 0;
+        __syncthreads();
+        smem[t] += add;
+        __syncthreads();
+    }
+    total = smem[kPlocThreads - 1];
+    const int incl = smem[t];
+    __syncthreads();
+    return incl - v;
+}
+
+__global__ void __launch_bounds__(kPlocThreads, 1)
+ploc_kernel(const unsigned long long *keys, const Aabb *bounds, int n, PlocNode *nodes, int *cl_a, int *cl_b, int *nn,
+            int *batch_start, int *n_batches_out, HostNode *out, int *prim_order, int do_collapse) {
+    __shared__ int scan[kPlocThreads];
+    const int t = threadIdx.x;
+    for (int i = t; i < n; i += kPlocThreads) {
+        PlocNode nd;
+        nd.box = bounds[(unsigned) keys[i]];
+        nd.left = nd.right = -1;
+        nd.size = 1;
+        nd.first = 0;
+        nd.cost = kCostPrim;
+        nd.collapsed = 0;
+        nodes[i] = nd;
+        cl_a[i] = i;
+    }
+    __syncthreads();
+    int m = n, n_alloc = n, n_batches = 0;
+    int *cin = cl_a, *cout = cl_b;
+    while (m > 1) {
+        if (t == 0) batch_start[n_batches] = n_alloc;
+        // 1. nearest neighbour within the radius (merged half-area), ties to the lower index
+        for (int i = t; i < m; i += kPlocThreads) {
+            const Aabb bi = nodes[cin[i]].box;
+            float best = FLT_MAX;
+            int bj = -1;
+            const int lo = max(0, i - kPlocRadius), hi = min(m - 1, i + kPlocRadius);
+            for (int j = lo; j <= hi; j++) {
+                if (j == i) continue;
+                const float a = half_area(merge(bi, nodes[cin[j]].box));
+                if (a < best) best = a, bj = j;
+            }
+            nn[i] = bj;
+        }
+        __syncthreads();
+        // 2. mutual pairs merge (the lower index keeps the slot); count new nodes and surviving clusters
+        const int per = (m + kPlocThreads - 1) / kPlocThreads;
+        const int b0 = min(m, t * per), b1 = min(m, b0 + per);
+        int my_new = 0, my_keep = 0;
+        for (int i = b0; i < b1; i++) {
+            const int j = nn[i];
+            const bool mutual = j >= 0 && nn[j] == i;
+            if (mutual && i < j) my_new++;
+            if (!(mutual && j < i)) my_keep++;
+        }
+        int tot_new, tot_keep;
+        int off_new = block_exclusive_scan(my_new, scan, tot_new);
+        int off_keep = block_exclusive_scan(my_keep, scan, tot_keep);
+        for (int i = b0; i < b1; i++) {
+            const int j = nn[i];
+            const bool mutual = j >= 0 && nn[j] == i;
+            if (mutual && j < i) continue;  // absorbed by its partner
+            int id = cin[i];
+            if (mutual) {
+                const int l = cin[i], r = cin[j];
+                const PlocNode nl = nodes[l], nr = nodes[r];
+                PlocNode nd;
+                nd.box = merge(nl.box, nr.box);
+                nd.left = l;
+                nd.right = r;
+                nd.size = nl.size + nr.size;
+                nd.first = 0;
+                const float a = half_area(nd.box);
+                float c_split = kCostNode + (a > 0.0f ? (half_area(nl.box) * nl.cost + half_area(nr.box) * nr.cost) / a : nl.cost + nr.cost);
+                const float c_leaf = kCostPrim * (float) nd.size;
+                nd.collapsed = 0;
+                if (do_collapse && nd.size <= kMaxLeafPrims && c_leaf <= c_split) {
+                    nd.collapsed = 1;
+                    c_split = c_leaf;
+                }
+                nd.cost = c_split;
+                id = n_alloc + off_new++;
+                nodes[id] = nd;
+            }
+            cout[off_keep++] = id;
+        }
+        __syncthreads();
+        n_alloc += tot_new;
+        m = tot_keep;
+        n_batches++;
+        int *tmp = cin;
+        cin = cout;
+        cout = tmp;
+        __syncthreads();
+    }
+    const int root = cin[0];  // == n_alloc - 1 == 2n - 2
+    if (t == 0) {
+        batch_start[n_batches] = n_alloc;
+        *n_batches_out = n_batches;
+        nodes[root].first = 0;
+        nodes[root].collapsed = 0;  // node 0 of the traversal tree must be an inner node
+    }
+    __syncthreads();
+    // 3. DFS positions, top-down, one creation batch at a time (children are always older than their parent)
+    for (int b = n_batches - 1; b >= 0; b--) {
+        for (int id = batch_start[b] + t; id < batch_start[b + 1]; id += kPlocThreads) {
+            const PlocNode nd = nodes[id];
+            nodes[nd.left].first = nd.first;
+            nodes[nd.right].first = nd.first + nodes[nd.left].size;
+        }
+        __syncthreads();
+    }
+    for (int i = t; i < n; i += kPlocThreads) prim_order[nodes[i].first] = (int) (unsigned) keys[i];
+    // 4. emit the 64-byte traversal nodes: internal id -> index (2n-2 - id), so the root lands at 0
+    for (int id = n + t; id < 2 * n - 1; id += kPlocThreads) {
+        const PlocNode nd = nodes[id];
+        HostNode h;
+        const int ch[2] = {nd.left, nd.right};
+        for (int c = 0; c < 2; c++) {
+            const PlocNode cn = nodes[ch[c]];
+            int ref;
+            if (ch[c] < n) ref = ~((cn.first << 3) | 0);
+            else if (cn.collapsed) ref = ~((cn.first << 3) | (cn.size - 1));
+            else ref = (2 * n - 2) - ch[c];
+            for (int k = 0; k < 3; k++) {
+                if (c == 0) h.c0mn[k] = cn.box.mn[k], h.c0mx[k] = cn.box.mx[k];
+                else h.c1mn[k] = cn.box.mn[k], h.c1mx[k] = cn.box.mx[k];
+            }
+            if (c == 0) h.child0 = ref;
+            else h.child1 = ref;
+        }
+        out[(2 * n - 2) - id] = h;
+    }
+}
+
 #define CK(call)                         \
     do {                                 \
         if ((call) != cudaSuccess) {     \
@@ -313,7 +474,7 @@ __global__ void emit_kernel(const unsigned long long *keys, const Aabb *bounds, 
 
 }  // namespace
 
-int build_bvh_lbvh_device(const std::vector<Aabb> &bounds, HostBvh &out, float *ms_device) {
+int build_bvh_device(const std::vector<Aabb> &bounds, HostBvh &out, float *ms_device, int use_ploc) {
     out = HostBvh();
     const int n = (int) bounds.size();
     if (n == 0) return 0;
@@ -340,10 +501,13 @@ int build_bvh_lbvh_device(const std::vector<Aabb> &bounds, HostBvh &out, float *
     int *d_leaf_parent = nullptr, *d_collapsed = nullptr;
     float *d_cost = nullptr;
     HostNode *d_out = nullptr;
+    PlocNode *d_ploc = nullptr;
+    int *d_cl_a = nullptr, *d_cl_b = nullptr, *d_nn = nullptr, *d_batch = nullptr, *d_order = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     auto cleanup = [&]() {
         cudaFree(d_bounds); cudaFree(d_box); cudaFree(d_cb); cudaFree(d_flags); cudaFree(d_keys); cudaFree(d_nodes);
         cudaFree(d_leaf_parent); cudaFree(d_collapsed); cudaFree(d_cost); cudaFree(d_out);
+        cudaFree(d_ploc); cudaFree(d_cl_a); cudaFree(d_cl_b); cudaFree(d_nn); cudaFree(d_batch); cudaFree(d_order);
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
     };
@@ -357,6 +521,14 @@ int build_bvh_lbvh_device(const std::vector<Aabb> &bounds, HostBvh &out, float *
     CK(cudaMalloc(&d_collapsed, sizeof(int) * n));
     CK(cudaMalloc(&d_cost, sizeof(float) * n));
     CK(cudaMalloc(&d_out, sizeof(HostNode) * n));
+    if (use_ploc) {
+        CK(cudaMalloc(&d_ploc, sizeof(PlocNode) * (2 * (size_t) n)));
+        CK(cudaMalloc(&d_cl_a, sizeof(int) * n));
+        CK(cudaMalloc(&d_cl_b, sizeof(int) * n));
+        CK(cudaMalloc(&d_nn, sizeof(int) * n));
+        CK(cudaMalloc(&d_batch, sizeof(int) * 4096));
+        CK(cudaMalloc(&d_order, sizeof(int) * n));
+    }
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
     CK(cudaMemcpy(d_bounds, bounds.data(), sizeof(Aabb) * n, cudaMemcpyHostToDevice));
@@ -376,9 +548,13 @@ int build_bvh_lbvh_device(const std::vector<Aabb> &bounds, HostBvh &out, float *
             bitonic_global_kernel<<<(n_pad / 2 + T - 1) / T, T>>>(d_keys, n_pad, j, k);
         bitonic_merge_local_kernel<<<n_pad / kSortTile, 1024>>>(d_keys, n_pad, k);
     }
-    radix_tree_kernel<<<(n - 1 + T - 1) / T, T>>>(d_keys, n, d_nodes, d_leaf_parent);
-    refit_kernel<<<(n + T - 1) / T, T>>>(d_keys, d_bounds, n, d_nodes, d_leaf_parent, d_box, d_cost, d_collapsed, d_flags, 1);
-    emit_kernel<<<(n - 1 + T - 1) / T, T>>>(d_keys, d_bounds, n, d_nodes, d_box, d_collapsed, d_out);
+    if (use_ploc) {
+        ploc_kernel<<<1, kPlocThreads>>>(d_keys, d_bounds, n, d_ploc, d_cl_a, d_cl_b, d_nn, d_batch, d_batch + 4095, d_out, d_order, 1);
+    } else {
+        radix_tree_kernel<<<(n - 1 + T - 1) / T, T>>>(d_keys, n, d_nodes, d_leaf_parent);
+        refit_kernel<<<(n + T - 1) / T, T>>>(d_keys, d_bounds, n, d_nodes, d_leaf_parent, d_box, d_cost, d_collapsed, d_flags, 1);
+        emit_kernel<<<(n - 1 + T - 1) / T, T>>>(d_keys, d_bounds, n, d_nodes, d_box, d_collapsed, d_out);
+    }
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     CK(cudaGetLastError());
@@ -389,7 +565,9 @@ int build_bvh_lbvh_device(const std::vector<Aabb> &bounds, HostBvh &out, float *
     std::vector<unsigned long long> keys((size_t) n);
     CK(cudaMemcpy(keys.data(), d_keys, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost));
     out.prim_order.resize((size_t) n);
-    for (int i = 0; i < n; i++) out.prim_order[i] = (int) (unsigned) keys[i];
+    if (use_ploc) CK(cudaMemcpy(out.prim_order.data(), d_order, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    else
+        for (int i = 0; i < n; i++) out.prim_order[i] = (int) (unsigned) keys[i];
     cleanup();
     out.sah_cost = bvh_sah_cost(out);
     return 0;

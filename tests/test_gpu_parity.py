@@ -96,15 +96,16 @@ def test_oracle_on_odd_configuration():
 
 @pytest.mark.parametrize("key", ["simple.aa1", "cornellbox_front.aa1", "marbles.aa1", "bunny.aa1", "horse_and_mug.aa1",
                                  "dragon_lowres.aa1", "low_poly_scene.aa1", "mirror_spheres.aa1", "Car.aa1"])
-def test_gpu_lbvh_builder(key):
-    """The BVH built on the GPU (Morton + bitonic sort + Karras + SAH collapse) must give the same frames: the tree
-    is only a filter, ties are settled by the reference-order ranks."""
+@pytest.mark.parametrize("builder", ["lbvh", "ploc"])
+def test_gpu_bvh_builders(key, builder):
+    """The BVHs built on the GPU (Morton + bitonic sort, then Karras' radix tree or PLOC clustering, SAH leaf collapse)
+    must give the same frames: the tree is only a filter, ties are settled by the reference-order ranks."""
     gold, m = H.golden_image(key)
     sc = H.golden_scene(m["scene"])
-    rt = tracer(m["scene"], builder=H.rt_b200.RT_BUILD_LBVH_GPU)
+    rt = tracer(m["scene"], builder={"lbvh": H.rt_b200.RT_BUILD_LBVH_GPU, "ploc": H.rt_b200.RT_BUILD_PLOC_GPU}[builder])
     img = rt.render(sc.camera(m["camera"]), 1)
     inf, ref_inf = rt.info(), tracer(m["scene"]).info()
-    print(key, H.diff_report(gold, img), f"lbvh: {inf.bvh_nodes} nodes depth {inf.bvh_max_depth} sah {inf.bvh_sah_cost:.1f} "
+    print(key, H.diff_report(gold, img), f"{builder}: {inf.bvh_nodes} nodes depth {inf.bvh_max_depth} sah {inf.bvh_sah_cost:.1f} "
           f"build {inf.ms_build_device:.3f} ms device, {rt.last_stats.ms_render:.3f} ms render | sah_host: {ref_inf.bvh_nodes} nodes "
           f"sah {ref_inf.bvh_sah_cost:.1f} build {ref_inf.ms_build_host:.1f} ms host")
     assert np.array_equal(img, gold)
