@@ -38,12 +38,14 @@ RT_DEV V3 clamp3(V3 c) {  // Vec3f::clamp(0, FLT_MAX), raytracer.cpp:451
 }  // namespace
 
 __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(const __grid_constant__ RenderParams p) {
-    __shared__ unsigned acc_all[kWarps2][kMaxP2 * kMaxP2 * 3];
+    // warp-private SSAA accumulators, sized per launch (P*P*3 words per warp; nothing when f == 1): whatever shared
+    // memory the kernel does not need stays L1 cache for the BVH
+    extern __shared__ unsigned acc_all[];
 
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
-    unsigned *acc = acc_all[threadIdx.x >> 5];
     const int f = p.f, P = p.P;
+    unsigned *acc = acc_all + (threadIdx.x >> 5) * (P * P * 3);
     const int items_per_tile = p.items_x * p.items_x;
     const V3 E0 = ld3(p.e), Q = ld3(p.q), U = ld3(p.u), Vv = ld3(p.v);
     const V3 Ia = ld3(p.ambient);
@@ -353,13 +355,20 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
 }
 
 int launch_render_v2(const RenderParams &p, int n_ctas, cudaStream_t stream) {
-    render_kernel_v2<<<n_ctas, kThreads2, 0, stream>>>(p);
+    const size_t smem = p.f > 1 ? (size_t) kWarps2 * p.P * p.P * 3 * sizeof(unsigned) : 0;
+    static bool configured = false;
+    if (!configured) {  // prefer L1 over shared memory: the kernel needs at most 12 KB of it
+        cudaFuncSetAttribute(render_kernel_v2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutDefault);
+        configured = true;
+    }
+    render_kernel_v2<<<n_ctas, kThreads2, smem, stream>>>(p);
     return (int) cudaGetLastError();
 }
 
 int render_kernel_v2_occupancy(int *ctas_per_sm, int *warps_per_cta) {
     *warps_per_cta = kWarps2;
-    return (int) cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, render_kernel_v2, kThreads2, 0);
+    return (int) cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, render_kernel_v2, kThreads2,
+                                                               (size_t) kWarps2 * kMaxP2 * kMaxP2 * 3 * sizeof(unsigned));
 }
 
 }  // namespace rtb

@@ -153,3 +153,56 @@ def test_full_size_config5(tmp_path):
     assert identical == (frep["equal"] == frep["pixels"])
     img2 = rt.render(cam, m["aa"])
     assert np.array_equal(img, img2)
+
+
+def test_cli_matches_reference_binary(tmp_path):
+    """`raytracer scene.xml` (default 2x2 SSAA, as the reference ships) writes the same PPM bytes as the reference's
+    own binary built by its Makefile flags (oracle/_ref/raytracer), and prints the reference's timing lines."""
+    import os
+    import subprocess
+    ours = os.path.join(H.PKG, "raytracer")
+    ref = os.path.join(H.ROOT, "oracle", "_ref", "raytracer")
+    if not (os.path.exists(ours) and os.path.exists(ref)):
+        pytest.skip("CLI binaries not built")
+    for scene in ("simple_reflectance", "cornellbox"):  # one and three cameras
+        xml = H.golden_scene_path(scene)
+        a, b = tmp_path / (scene + "_ours"), tmp_path / (scene + "_ref")
+        a.mkdir()
+        b.mkdir()
+        out = subprocess.run([ours, xml, "--stats"], cwd=a, capture_output=True, text=True, check=True).stdout
+        subprocess.run([ref, xml], cwd=b, capture_output=True, text=True, check=True)
+        assert "Planted trees in" in out and "Rendered in" in out and "Total:" in out
+        assert "Super Sampling Anti aliasing is enabled. (2*2x)" in out
+        names = sorted(os.listdir(b))
+        assert names and sorted(os.listdir(a)) == names
+        for n in names:
+            assert open(a / n, "rb").read() == open(b / n, "rb").read(), (scene, n)
+
+
+def test_single_process_multi_gpu():
+    """rt_render_multi (what `raytracer --gpus N` uses): one handle per device, interleaved tiles, peer copies to
+    device 0, one D2H — the frame must equal the single-GPU frame.  Needs >= 2 GPUs (gpurun --gpus 2)."""
+    import ctypes as C
+    import torch
+    n = min(torch.cuda.device_count(), 4)
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    L = H.rt_b200.cuda_lib()
+    sc = H.golden_scene("horse_and_mug")
+    cam = sc.camera(0, 700, 390)
+    single = tracer("horse_and_mug").render(cam, 3)
+    want = tracer("horse_and_mug").last_stats
+    handles = []
+    for d in range(n):
+        assert L.rt_set_device(d) == 0
+        handles.append(H.RayTracer(sc))
+    L.rt_set_device(0)
+    arr = (C.c_void_p * n)(*[h.h for h in handles])
+    out = np.zeros_like(single)
+    st = H.RtStats()
+    rc = L.rt_render_multi(arr, n, C.byref(cam), 3, out.ctypes.data, C.byref(st))
+    assert rc == 0, L.rt_last_error()
+    assert np.array_equal(out, single)
+    assert (st.primary_rays, st.reflection_rays, st.shadow_rays) == (want.primary_rays, want.reflection_rays, want.shadow_rays)
+    for h in handles:
+        h.close()
