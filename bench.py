@@ -333,15 +333,21 @@ def run_b200(args):
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tr.get(f"{args.scene}:{args.width}x{args.height}:{args.aa}:{world}", {}).get("bytes")
+        except Exception:
+            pass
         roofline = None
         if flop_ray:
             achieved = kernel_rays_per_s * flop_ray / 1e12
-            roofline = {"bound": "fp32-issue (neither hbm nor tensor: the scene is L2-resident, SURVEY.md 8d)",
-                        "kernel": "rtb::render_kernel", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+            roofline = {"bound": "fp32_issue", "bound_note": "neither hbm nor tensor: the scene is L2-resident and the path is not a contraction (SURVEY.md 8d)",
+                        "kernel": "rtb::render_kernel_v2", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
                         "frac": achieved / peak_tflops,
                         "peak_source": f"{n_sm} SMs x 128 FP32 lanes x {f_clk / 1e6:.0f} MHz observed under load (non-FMA; no measured FP32 peak in MEASURED_PEAKS.json)",
                         "algorithmic_flop_per_ray": flop_ray, "rays_per_launch": rays // world, "kernel_ms": kernel_ms,
-                        "traffic": None,
+                        "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)",
                         "hbm": {"algorithmic_bytes_per_launch": frame_bytes // world, "achieved_gbs": frame_bytes / world / (kernel_ms * 1e-3) / 1e9,
                                 "peak_gbs": hbm_peak, "peak_source": "measured" if peaks else "fallback",
                                 "frac": frame_bytes / world / (kernel_ms * 1e-3) / 1e9 / hbm_peak},

@@ -26,7 +26,7 @@ constexpr int kThreads2 = kWarps2 * 32;
 constexpr int kMaxP2 = 16;  // warp tile side in pixels when f > 1 (acc size); f == 1 writes pixels directly
 
 #ifndef RT_MIN_CTAS2
-#define RT_MIN_CTAS2 6
+#define RT_MIN_CTAS2 7
 #endif
 
 enum Phase : int { kIdle = 0, kClosest = 1, kShadow = 2 };
