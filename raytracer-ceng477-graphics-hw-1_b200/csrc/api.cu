@@ -441,6 +441,19 @@ int rt_scene_create(const RtSceneDesc *desc, const RtBuildOptions *opts, RtScene
     }
     const float sah = bvh_sah_cost(bvh);
     pad_boxes(bvh, bounds);
+    // A single-primitive scene has a root with one real child.  The missing child becomes a leaf over a dummy
+    // all-zero triangle (slot np: detA = 0, every comparison on NaN fails, it can never report a hit), so the
+    // traversal loop needs no "empty child" test.
+    for (auto &n: bvh.nodes) {
+        if (n.child1 == kEmptyChild) {
+            n.child1 = ~((np << 3) | 0);
+            for (int k = 0; k < 3; k++) n.c1mn[k] = n.c0mn[k], n.c1mx[k] = n.c0mx[k];
+        }
+        if (n.child0 == kEmptyChild) {
+            n.child0 = ~((np << 3) | 0);
+            for (int k = 0; k < 3; k++) n.c0mn[k] = n.c1mn[k], n.c0mx[k] = n.c1mx[k];
+        }
+    }
 
     // stage SoA buffers
     std::vector<float4> nodes(bvh.nodes.size() * 4);
@@ -452,7 +465,7 @@ int rt_scene_create(const RtSceneDesc *desc, const RtBuildOptions *opts, RtScene
         nodes[4 * i + 3] = make_float4(__builtin_bit_cast(float, n.child0), __builtin_bit_cast(float, n.child1), 0.f, 0.f);
     }
     auto bits = [](int v) { return __builtin_bit_cast(float, v); };
-    std::vector<float4> prims((size_t) np * 3);
+    std::vector<float4> prims((size_t) (np + 1) * 3, make_float4(0.f, 0.f, 0.f, 0.f));
     for (int sidx = 0; sidx < np; sidx++) {
         const int id = bvh.prim_order[sidx];
         if (id < nt) {

@@ -258,3 +258,97 @@ def golden_image(key):
         raw = f.read()
     rows = len(m["rows"]) if "rows" in m else m["height"]
     return np.frombuffer(raw, np.uint8).reshape(rows, m["width"], 3), m
+
+
+# ----------------------------------------------------------------------------- seeded synthetic scenes
+
+
+def random_scene(seed, n_tris=40, n_spheres=4, n_lights=2, max_depth=3, width=96, height=64, flat_fraction=0.3,
+                 camera_inside_sphere=False):
+    """A seeded triangle/sphere soup with the hard cases mixed in: axis-aligned (zero-thickness) triangles, triangles
+    sharing edges and vertices (exact-t ties), a degenerate triangle, mirrors, lights inside geometry."""
+    rng = np.random.default_rng(seed)
+    verts, tris = [], []
+
+    def add_vertex(p):
+        verts.append([float(np.float32(x)) for x in p])
+        return len(verts)
+
+    n_mat = 5
+    for i in range(n_tris):
+        c = rng.uniform(-4, 4, 3) + np.array([0, 0, -10.0])
+        a, b, d = c + rng.uniform(-1.5, 1.5, 3), c + rng.uniform(-1.5, 1.5, 3), c + rng.uniform(-1.5, 1.5, 3)
+        if rng.random() < flat_fraction:  # axis-aligned: flat bounding box
+            ax = int(rng.integers(0, 3))
+            v = np.round(c[ax] * 4) / 4
+            a[ax] = b[ax] = d[ax] = v
+        ia, ib, ic = add_vertex(a), add_vertex(b), add_vertex(d)
+        tris.append([ia, ib, ic, int(rng.integers(1, n_mat + 1))])
+        if rng.random() < 0.4:  # a neighbour sharing the edge (b, d): rays through the edge tie exactly
+            e = c + rng.uniform(-1.5, 1.5, 3)
+            tris.append([ib, add_vertex(e), ic, int(rng.integers(1, n_mat + 1))])
+    # a big floor quad (two coplanar triangles) and a degenerate triangle
+    f = [add_vertex(p) for p in ([-8, -4, -2], [8, -4, -2], [8, -4, -18], [-8, -4, -18])]
+    tris += [[f[0], f[1], f[2], 1], [f[2], f[3], f[0], 1], [f[0], f[0], f[1], 2]]
+    sph_ids, sph_r = [], []
+    for i in range(n_spheres):
+        c = rng.uniform(-3, 3, 3) + np.array([0, 0, -9.0])
+        sph_ids.append([int(rng.integers(1, n_mat + 1)), add_vertex(c)])
+        sph_r.append(float(rng.uniform(0.4, 1.6)))
+    if camera_inside_sphere:
+        sph_ids.append([3, add_vertex([0.1, 0.0, 0.3])])
+        sph_r.append(2.5)
+    m13 = np.zeros((n_mat, 13), np.float32)
+    m13[:, 0:3] = rng.uniform(0, 1, (n_mat, 3))
+    m13[:, 3:6] = rng.uniform(0, 1, (n_mat, 3))
+    m13[:, 6:9] = rng.uniform(0, 1, (n_mat, 3))
+    m13[:, 9:12] = rng.uniform(0, 0.9, (n_mat, 3))
+    m13[:, 12] = rng.choice([1, 2, 3, 10, 50, 100, 2.5], n_mat)
+    mirror = (rng.random(n_mat) < 0.5).astype(np.int32)
+    lights = np.zeros((n_lights, 6), np.float32)
+    lights[:, 0:3] = rng.uniform(-6, 6, (n_lights, 3)) + np.array([0, 4, -6.0])
+    lights[:, 3:6] = rng.uniform(200, 2000, (n_lights, 3))
+    cam = RtCamera(RtVec3(0.1, 0.2, 0.5), RtVec3(0.02, -0.05, -1.0), RtVec3(0.0, 1.0, 0.05), -1.0, 1.0, -0.66, 0.66, 1.0, width, height)
+    return Scene(np.array(verts, np.float32), np.array(tris, np.int32), np.array(sph_ids, np.int32).reshape(-1, 2), np.array(sph_r, np.float32),
+                 m13, mirror, lights, [20.0, 25.0, 30.0], float(np.float32(rng.choice([1e-3, 1e-4, 1e-2]))), [10, 20, 30], max_depth,
+                 [(cam, f"random_{seed}.ppm")])
+
+
+def scene_to_xml(sc, path):
+    """Writes a Scene in the reference's XML grammar (floats with 9 significant digits round-trip through >>)."""
+    d = sc.desc
+
+    def v(a):
+        return " ".join(repr(float(np.float32(x))) if not float(x).is_integer() else str(int(x)) for x in a)
+
+    def f32(x):
+        return np.format_float_scientific(np.float32(x), unique=True)
+    out = ["<Scene>", f"<BackgroundColor>{d.background[0]} {d.background[1]} {d.background[2]}</BackgroundColor>",
+           f"<ShadowRayEpsilon>{f32(d.shadow_ray_epsilon)}</ShadowRayEpsilon>", f"<MaxRecursionDepth>{d.max_recursion_depth}</MaxRecursionDepth>", "<Cameras>"]
+    for cam, name in sc.cameras:
+        out += ["<Camera>", f"<Position>{f32(cam.position.x)} {f32(cam.position.y)} {f32(cam.position.z)}</Position>",
+                f"<Gaze>{f32(cam.gaze.x)} {f32(cam.gaze.y)} {f32(cam.gaze.z)}</Gaze>", f"<Up>{f32(cam.up.x)} {f32(cam.up.y)} {f32(cam.up.z)}</Up>",
+                f"<NearPlane>{f32(cam.l)} {f32(cam.r)} {f32(cam.b)} {f32(cam.t)}</NearPlane>", f"<NearDistance>{f32(cam.near_distance)}</NearDistance>",
+                f"<ImageResolution>{cam.image_width} {cam.image_height}</ImageResolution>", f"<ImageName>{name}</ImageName>", "</Camera>"]
+    out += ["</Cameras>", "<Lights>", f"<AmbientLight>{f32(d.ambient_light.x)} {f32(d.ambient_light.y)} {f32(d.ambient_light.z)}</AmbientLight>"]
+    for l in sc.lights:
+        out += ["<PointLight>", "<Position>" + " ".join(f32(x) for x in l[0:3]) + "</Position>",
+                "<Intensity>" + " ".join(f32(x) for x in l[3:6]) + "</Intensity>", "</PointLight>"]
+    out += ["</Lights>", "<Materials>"]
+    for m in sc.materials:
+        fm = m["f"]
+        out += ['<Material type="mirror">' if m["is_mirror"] else "<Material>",
+                "<AmbientReflectance>" + " ".join(f32(x) for x in fm[0:3]) + "</AmbientReflectance>",
+                "<DiffuseReflectance>" + " ".join(f32(x) for x in fm[3:6]) + "</DiffuseReflectance>",
+                "<SpecularReflectance>" + " ".join(f32(x) for x in fm[6:9]) + "</SpecularReflectance>",
+                "<MirrorReflectance>" + " ".join(f32(x) for x in fm[9:12]) + "</MirrorReflectance>",
+                f"<PhongExponent>{f32(fm[12])}</PhongExponent>", "</Material>"]
+    out += ["</Materials>", "<VertexData>"] + [" ".join(f32(x) for x in p) for p in sc.vertices] + ["</VertexData>", "<Objects>"]
+    for t in sc.triangles:  # every triangle as a <Triangle>: the flat list order is then the file order
+        out += ["<Triangle>", f"<Material>{t[3]}</Material>", f"<Indices>{t[0]} {t[1]} {t[2]}</Indices>", "</Triangle>"]
+    for s in sc.spheres:
+        out += ["<Sphere>", f"<Material>{s['material_id']}</Material>", f"<Center>{s['center_vertex_id']}</Center>",
+                f"<Radius>{f32(s['radius'])}</Radius>", "</Sphere>"]
+    out += ["</Objects>", "</Scene>"]
+    with open(path, "w") as fo:
+        fo.write("\n".join(out))

@@ -206,3 +206,70 @@ def test_single_process_multi_gpu():
     assert (st.primary_rays, st.reflection_rays, st.shadow_rays) == (want.primary_rays, want.reflection_rays, want.shadow_rays)
     for h in handles:
         h.close()
+
+
+@pytest.mark.parametrize("seed", list(range(1, 13)))
+def test_seeded_scenes_against_oracle(seed):
+    """Seeded triangle/sphere soups with the hard cases mixed in (zero-thickness boxes, exact-t ties on shared
+    edges, a degenerate triangle, mirrors, the camera inside a sphere on even seeds), all three kernels and all
+    three BVH builders against the oracle on the box's CPU: byte identity and equal ray counts."""
+    sc = H.random_scene(seed, n_tris=30 + 7 * seed, camera_inside_sphere=(seed % 2 == 0), max_depth=seed % 5, width=120, height=72)
+    cam = sc.camera(0)
+    aa = 1 + seed % 3
+    want, ost = H.OracleScene(sc).render(cam, aa)
+    import os
+    builders = (H.rt_b200.RT_BUILD_PLOC_GPU, H.rt_b200.RT_BUILD_LBVH_GPU, H.rt_b200.RT_BUILD_SAH_HOST)
+    for kernel, builder in (("2", builders[seed % 3]), ("1", builders[(seed + 1) % 3]), ("3", builders[(seed + 2) % 3])):
+        os.environ["RT_B200_KERNEL"] = kernel
+        try:
+            rt = H.RayTracer(sc, builder=builder)
+        finally:
+            os.environ.pop("RT_B200_KERNEL", None)
+        got = rt.render(cam, aa)
+        st = rt.last_stats
+        rep = H.diff_report(want, got)
+        assert rep["equal"] == rep["pixels"], (seed, kernel, builder, rep)
+        assert (st.primary_rays, st.reflection_rays, st.shadow_rays, st.shadow_occluded) == \
+            (ost.primary_rays, ost.reflection_rays, ost.shadow_rays, ost.shadow_occluded), (seed, kernel, builder)
+        rt.close()
+
+
+def _tiny_scene(tris, spheres=(), lights=((0, 5, 0, 500, 500, 500),), depth=2, mirror=1):
+    verts = [[-1, -1, -5], [1, -1, -5], [0, 1, -5], [0, 0, -3]]
+    m13 = [[0.2, 0.2, 0.2, 0.5, 0.5, 0.5, 0.3, 0.3, 0.3, 0.8, 0.8, 0.8, 10]]
+    cam = H.RtCamera(H.RtVec3(0, 0, 0), H.RtVec3(0, 0, -1), H.RtVec3(0, 1, 0), -1, 1, -1, 1, 1, 33, 17)
+    return H.Scene(np.array(verts, np.float32), np.array(tris, np.int32).reshape(-1, 4), np.array([s[:2] for s in spheres], np.int32).reshape(-1, 2),
+                   np.array([s[2] for s in spheres], np.float32), m13, [mirror], np.array(lights, np.float32).reshape(-1, 6), [10, 10, 10], 1e-3,
+                   [7, 8, 9], depth, [(cam, "tiny.ppm")])
+
+
+@pytest.mark.parametrize("case", ["empty", "no_lights", "one_triangle", "one_sphere", "depth0", "depth32", "one_pixel", "aa64"])
+def test_edge_cases_against_oracle(case):
+    """Degenerate inputs the reference handles implicitly: no primitives (background only), no lights (ambient
+    only), single-primitive trees, recursion depth 0 and the supported maximum, a 1x1 frame, a 64x64 sample grid."""
+    sc = {"empty": lambda: _tiny_scene([]), "no_lights": lambda: _tiny_scene([[1, 2, 3, 1]], lights=()),
+          "one_triangle": lambda: _tiny_scene([[1, 2, 3, 1]]), "one_sphere": lambda: _tiny_scene([], spheres=[(1, 4, 0.7)]),
+          "depth0": lambda: _tiny_scene([[1, 2, 3, 1]], spheres=[(1, 4, 0.7)], depth=0),
+          "depth32": lambda: _tiny_scene([[1, 2, 3, 1]], spheres=[(1, 4, 0.7)], depth=32),
+          "one_pixel": lambda: _tiny_scene([[1, 2, 3, 1]]), "aa64": lambda: _tiny_scene([[1, 2, 3, 1]], spheres=[(1, 4, 0.7)])}[case]()
+    cam = sc.camera(0, 1, 1) if case == "one_pixel" else (sc.camera(0, 5, 3) if case == "aa64" else sc.camera(0))
+    aa = 64 if case == "aa64" else 2
+    want, ost = H.OracleScene(sc).render(cam, aa)
+    rt = H.RayTracer(sc)
+    got = rt.render(cam, aa)
+    assert np.array_equal(want, got), H.diff_report(want, got)
+    assert rt.last_stats.total_rays == ost.total_rays
+    rt.close()
+
+
+def test_argument_errors():
+    """The C-ABI returns error codes instead of crashing: bad ids, bad AA factor, unsupported recursion depth."""
+    sc = _tiny_scene([[1, 2, 9, 1]])  # vertex id 9 does not exist
+    with pytest.raises(H.rt_b200.RtError, match="vertex id out of range"):
+        H.RayTracer(sc)
+    with pytest.raises(H.rt_b200.RtError, match="max_recursion_depth"):
+        H.RayTracer(_tiny_scene([[1, 2, 3, 1]], depth=33))
+    rt = H.RayTracer(_tiny_scene([[1, 2, 3, 1]]))
+    with pytest.raises(H.rt_b200.RtError, match="aa_factor"):
+        rt.render(rt.scene.camera(0), 0)
+    rt.close()

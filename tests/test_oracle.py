@@ -70,3 +70,21 @@ def test_oracle_matches_live_reference_on_unseen_configuration():
     got, _ = H.OracleScene(sc).render(sc.camera(0, 101, 67), 3)
     ref.close()
     assert np.array_equal(want, got)
+
+
+@pytest.mark.skipif(not H.ref_available(), reason="oracle/_ref/libref.so not built (needs /root/reference)")
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_oracle_matches_live_reference_on_seeded_scenes(seed, tmp_path):
+    """Seeded triangle/sphere soups (flat boxes, shared edges, a degenerate triangle, mirrors, the camera inside a
+    sphere for even seeds) written as XML, rendered by the unmodified reference and by the oracle: byte identity.
+    Also checks the product's XML loader on a file the reference's loader parses."""
+    sc = H.random_scene(seed, camera_inside_sphere=(seed % 2 == 0), max_depth=seed % 4)
+    xml = str(tmp_path / f"random_{seed}.xml")
+    H.scene_to_xml(sc, xml)
+    ref = H.RefScene(xml)
+    assert ref.to_scene().digest() == H.load_scene_xml(xml).digest()
+    for aa in (1, 3):
+        want, _ = ref.render(0, aa)
+        got, _ = H.OracleScene(ref.to_scene()).render(ref.to_scene().camera(0), aa)
+        assert np.array_equal(want, got), (seed, aa, H.diff_report(want, got))
+    ref.close()
