@@ -356,11 +356,6 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
 
 int launch_render_v2(const RenderParams &p, int n_ctas, cudaStream_t stream) {
     const size_t smem = p.f > 1 ? (size_t) kWarps2 * p.P * p.P * 3 * sizeof(unsigned) : 0;
-    static bool configured = false;
-    if (!configured) {  // prefer L1 over shared memory: the kernel needs at most 12 KB of it
-        cudaFuncSetAttribute(render_kernel_v2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutDefault);
-        configured = true;
-    }
     render_kernel_v2<<<n_ctas, kThreads2, smem, stream>>>(p);
     return (int) cudaGetLastError();
 }
