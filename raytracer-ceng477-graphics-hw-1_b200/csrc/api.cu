@@ -425,8 +425,11 @@ int rt_scene_create(const RtSceneDesc *desc, const RtBuildOptions *opts, RtScene
 
     HostBvh bvh;
     float ms_device = 0;
+    double ms_device_wall = 0;  // includes CUDA context creation on the first call; not host build work
     if (builder == RT_BUILD_LBVH_GPU || builder == RT_BUILD_PLOC_GPU) {
+        const double td0 = now_ms();
         int e = build_bvh_device(bounds, bvh, &ms_device, builder == RT_BUILD_PLOC_GPU);
+        ms_device_wall = now_ms() - td0;
         if (e != 0) {
             delete s;
             return fail(RT_ERR_CUDA, "device BVH build failed");
@@ -619,7 +622,7 @@ int rt_scene_create(const RtSceneDesc *desc, const RtBuildOptions *opts, RtScene
     inf.ref_tree_leaves = rstats.leaves;
     inf.ref_tree_max_leaf = rstats.max_leaf;
     inf.ref_tree_max_depth = rstats.max_depth;
-    inf.ms_build_host = (float) (t1 - t0);
+    inf.ms_build_host = (float) (t1 - t0 - ms_device_wall);
     inf.ms_build_device = ms_device;
     inf.bvh_sah_cost = sah;
     inf.builder = builder;

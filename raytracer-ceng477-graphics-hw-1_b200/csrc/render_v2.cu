@@ -28,6 +28,9 @@ constexpr int kMaxP2 = 16;  // warp tile side in pixels when f > 1 (acc size); f
 #ifndef RT_MIN_CTAS2
 #define RT_MIN_CTAS2 7
 #endif
+#ifndef RT_WHILE_WHILE
+#define RT_WHILE_WHILE 1
+#endif
 
 enum Phase : int { kIdle = 0, kClosest = 1, kShadow = 2 };
 
@@ -149,7 +152,13 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
                     stack[sp++] = kSentinel;
                     int node = 0;
                     while (node != kSentinel) {
+#if RT_WHILE_WHILE
+                        // "while-while": lanes keep descending until every lane of the warp holds a leaf (or is
+                        // done), then the warp runs the primitive tests together
+                        while ((unsigned) node < (unsigned) kSentinel) {
+#else
                         if (node >= 0) {
+#endif
                             const float4 n0 = __ldg(&p.nodes[4 * node]);
                             const float4 n1 = __ldg(&p.nodes[4 * node + 1]);
                             const float4 n2 = __ldg(&p.nodes[4 * node + 2]);
@@ -171,7 +180,12 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
                             } else {
                                 node = stack[--sp];
                             }
+#if RT_WHILE_WHILE
+                        }
+                        if (node < 0) {
+#else
                         } else {
+#endif
                             const int enc = ~node;
                             const int first = enc >> 3, count = (enc & 7) + 1;
                             node = stack[--sp];
