@@ -107,14 +107,16 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------- reference arm
 
 
-def cpu_sample_rows(args, threads):
+def cpu_sample_rows(args, threads, passes=1):
     """Bounded sample of the workload for the CPU: every k-th sub-sample row of the (width*aa) x (height*aa) grid,
-    sized for roughly 10-30 s of CPU work (~2.5 Mrays/s per core, 3.44 rays per sub-sample on horse_and_mug)."""
+    sized for roughly 15 s of CPU work per pass (~2.5 Mrays/s per core, 3.44 rays per sub-sample on horse_and_mug)
+    and at most ~2 minutes over all passes of a run."""
     total_rows = args.height * args.aa
     if args.cpu_rows > 0:
         n = min(args.cpu_rows, total_rows)
     else:
-        target_rays = 15.0 * 2.5e6 * max(1, threads)
+        seconds = max(2.0, min(15.0, 120.0 / max(1, passes)))
+        target_rays = seconds * 2.5e6 * max(1, threads)
         n = int(target_rays / (3.44 * args.width * args.aa))
         n = max(4, min(n, total_rows))
     stride = max(1, total_rows // n)
@@ -127,7 +129,7 @@ def reference_sample(args, steps, warmup):
     /root/reference, else the C port) on the sample; ray count of the sample from the C port (same decisions)."""
     import harness as H
     threads = os.cpu_count() or 8
-    row0, stride, n_rows = cpu_sample_rows(args, threads)
+    row0, stride, n_rows = cpu_sample_rows(args, threads, passes=steps + warmup + 1)
     sc = H.golden_scene(args.scene)
     cam = sc.camera(0, args.width, args.height)
     orc = H.OracleScene(sc)
