@@ -438,6 +438,13 @@ int rt_scene_create(const RtSceneDesc *desc, const RtBuildOptions *opts, RtScene
         build_bvh_sah_host(bounds, bvh);
     }
     bvh.max_depth = tree_depth(bvh);
+    if (bvh.max_depth > 60 && builder != RT_BUILD_SAH_HOST) {
+        // a pathological primitive order made the clustered tree too deep for the traversal stack: the host
+        // builder splits at the median when the SAH finds nothing and stays O(log n) deep
+        builder = RT_BUILD_SAH_HOST;
+        build_bvh_sah_host(bounds, bvh);
+        bvh.max_depth = tree_depth(bvh);
+    }
     if (bvh.max_depth > 60) {
         delete s;
         return fail(RT_ERR_STATE, "BVH deeper than the traversal stack");
