@@ -14,6 +14,7 @@
 // reference-order ranks, so nothing here needs to mimic the reference's midpoint splits.
 #include <cfloat>
 #include <cstdint>
+#include <cstdlib>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -310,7 +311,8 @@ __global__ void emit_kernel(const unsigned long long *keys, const Aabb *bounds, 
 // list is compacted with a block-wide prefix sum.  SAH cost / leaf collapse are evaluated when a node is
 // created (children always exist already); DFS positions are then pushed down batch by batch so that every
 // subtree owns a contiguous range of the final primitive order.
-constexpr int kPlocRadius = 16;
+constexpr int kPlocRadiusDefault = 16;
+constexpr float kPlocLeafCost = 1.0f;  // per-primitive cost in the collapse decision (tools/ploc_tune.py: 1.0 beats 1.6 and 2.5)
 constexpr int kPlocThreads = 1024;
 
 struct PlocNode {
@@ -341,7 +343,8 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *smem, int &total
 
 __global__ void __launch_bounds__(kPlocThreads, 1)
 ploc_kernel(const unsigned long long *keys, const Aabb *bounds, int n, PlocNode *nodes, int *cl_a, int *cl_b, int *nn,
-            int *batch_start, int *n_batches_out, HostNode *out, int *prim_order, int do_collapse) {
+            int *batch_start, int *n_batches_out, HostNode *out, int *prim_order, int do_collapse, int kPlocRadius,
+            float cost_prim) {
     __shared__ int scan[kPlocThreads];
     const int t = threadIdx.x;
     for (int i = t; i < n; i += kPlocThreads) {
@@ -350,7 +353,7 @@ ploc_kernel(const unsigned long long *keys, const Aabb *bounds, int n, PlocNode 
         nd.left = nd.right = -1;
         nd.size = 1;
         nd.first = 0;
-        nd.cost = kCostPrim;
+        nd.cost = cost_prim;
         nd.collapsed = 0;
         nodes[i] = nd;
         cl_a[i] = i;
@@ -403,7 +406,7 @@ ploc_kernel(const unsigned long long *keys, const Aabb *bounds, int n, PlocNode 
                 nd.first = 0;
                 const float a = half_area(nd.box);
                 float c_split = kCostNode + (a > 0.0f ? (half_area(nl.box) * nl.cost + half_area(nr.box) * nr.cost) / a : nl.cost + nr.cost);
-                const float c_leaf = kCostPrim * (float) nd.size;
+                const float c_leaf = cost_prim * (float) nd.size;
                 nd.collapsed = 0;
                 if (do_collapse && nd.size <= kMaxLeafPrims && c_leaf <= c_split) {
                     nd.collapsed = 1;
@@ -549,7 +552,12 @@ int build_bvh_device(const std::vector<Aabb> &bounds, HostBvh &out, float *ms_de
         bitonic_merge_local_kernel<<<n_pad / kSortTile, 1024>>>(d_keys, n_pad, k);
     }
     if (use_ploc) {
-        ploc_kernel<<<1, kPlocThreads>>>(d_keys, d_bounds, n, d_ploc, d_cl_a, d_cl_b, d_nn, d_batch, d_batch + 4095, d_out, d_order, 1);
+        // tuning knobs for experiments (tools/builder_ab.py): search radius and the leaf cost of the SAH collapse
+        const char *er = getenv("RT_B200_PLOC_RADIUS"), *ec = getenv("RT_B200_PLOC_LEAF_COST");
+        const int radius = er ? atoi(er) : kPlocRadiusDefault;
+        const float cost_prim = ec ? (float) atof(ec) : kPlocLeafCost;
+        ploc_kernel<<<1, kPlocThreads>>>(d_keys, d_bounds, n, d_ploc, d_cl_a, d_cl_b, d_nn, d_batch, d_batch + 4095, d_out, d_order,
+                                         cost_prim < 1e9f, radius, cost_prim);
     } else {
         radix_tree_kernel<<<(n - 1 + T - 1) / T, T>>>(d_keys, n, d_nodes, d_leaf_parent);
         refit_kernel<<<(n + T - 1) / T, T>>>(d_keys, d_bounds, n, d_nodes, d_leaf_parent, d_box, d_cost, d_collapsed, d_flags, 1);
