@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -469,9 +470,18 @@ int rt_scene_create(const RtSceneDesc *desc, const RtBuildOptions *opts, RtScene
     std::vector<float4> nodes(bvh.nodes.size() * 4);
     for (size_t i = 0; i < bvh.nodes.size(); i++) {
         const HostNode &n = bvh.nodes[i];
-        nodes[4 * i + 0] = make_float4(n.c0mn[0], n.c0mx[0], n.c0mn[1], n.c0mx[1]);
-        nodes[4 * i + 1] = make_float4(n.c1mn[0], n.c1mx[0], n.c1mn[1], n.c1mx[1]);
-        nodes[4 * i + 2] = make_float4(n.c0mn[2], n.c0mx[2], n.c1mn[2], n.c1mx[2]);
+        // per axis: (centre, half-extent) of the padded child box; the half-extent is rounded up so that the
+        // stored box still contains the padded one (device_common.cuh slab())
+        float c0[3], h0[3], c1[3], h1[3];
+        for (int k = 0; k < 3; k++) {
+            c0[k] = 0.5f * (n.c0mn[k] + n.c0mx[k]);
+            c1[k] = 0.5f * (n.c1mn[k] + n.c1mx[k]);
+            h0[k] = std::max(n.c0mx[k] - c0[k], c0[k] - n.c0mn[k]) * 1.000001f + std::fabs(c0[k]) * 2e-7f;
+            h1[k] = std::max(n.c1mx[k] - c1[k], c1[k] - n.c1mn[k]) * 1.000001f + std::fabs(c1[k]) * 2e-7f;
+        }
+        nodes[4 * i + 0] = make_float4(c0[0], h0[0], c0[1], h0[1]);
+        nodes[4 * i + 1] = make_float4(c1[0], h1[0], c1[1], h1[1]);
+        nodes[4 * i + 2] = make_float4(c0[2], h0[2], c1[2], h1[2]);
         nodes[4 * i + 3] = make_float4(__builtin_bit_cast(float, n.child0), __builtin_bit_cast(float, n.child1), 0.f, 0.f);
     }
     auto bits = [](int v) { return __builtin_bit_cast(float, v); };

@@ -13,9 +13,10 @@ namespace rtb {
 // shipped scene, L2-resident; all records are 16-byte aligned so every fetch is one LDG.128).
 //
 //  nodes      float4[4 * n_nodes]   BVH2, both children's boxes in the parent (64 B per node):
-//                                    [0] = c0.min.x c0.max.x c0.min.y c0.max.y
-//                                    [1] = c1.min.x c1.max.x c1.min.y c1.max.y
-//                                    [2] = c0.min.z c0.max.z c1.min.z c1.max.z
+//                                   (per axis centre c and half-extent h of the padded box)
+//                                    [0] = c0.c.x c0.h.x c0.c.y c0.h.y
+//                                    [1] = c1.c.x c1.h.x c1.c.y c1.h.y
+//                                    [2] = c0.c.z c0.h.z c1.c.z c1.h.z
 //                                    [3] = bits(child0) bits(child1) - -
 //                                   child >= 0: inner node index; child < 0: leaf, ~child = (first << 3) | (count - 1)
 //                                   into `prims`; kEmptyChild: no child (box inverted, never hit)
