@@ -40,7 +40,7 @@ RT_DEV bool traverse(const RenderParams &p, const Ray &r, float limit, float &tb
                         return true;
                     }
                 } else {
-                    closest_update(p, r.oct, t, prim, tbest, pbest, tsecond);
+                    closest_update(p, r, t, prim, tbest, pbest, tsecond);
                 }
             }
         }
@@ -90,7 +90,7 @@ RT_DEV bool traverse(const RenderParams &p, const Ray &r, float limit, float &tb
                             return true;
                         }
                     } else {
-                        closest_update(p, r.oct, t, prim, tbest, pbest, tsecond);
+                        closest_update(p, r, t, prim, tbest, pbest, tsecond);
                     }
                 }
             }

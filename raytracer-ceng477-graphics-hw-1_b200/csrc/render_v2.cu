@@ -28,6 +28,9 @@ constexpr int kMaxP2 = 16;  // warp tile side in pixels when f > 1 (acc size); f
 #ifndef RT_MIN_CTAS2
 #define RT_MIN_CTAS2 7
 #endif
+#ifndef RT_BRANCHLESS_STEP
+#define RT_BRANCHLESS_STEP 1
+#endif
 #ifndef RT_WHILE_WHILE
 #define RT_WHILE_WHILE 1
 #endif
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
                                     pbest = prim;
                                 }
                             } else {
-                                closest_update(p, ray.oct, t, prim, tbest, pbest, tsecond);
+                                closest_update(p, ray, t, prim, tbest, pbest, tsecond);
                             }
                         }
                     }
@@ -169,6 +172,14 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
                             const bool h0 = tmax0 >= fmaxf(tmin0, 0.0f) && tmin0 <= tbest;
                             const bool h1 = tmax1 >= fmaxf(tmin1, 0.0f) && tmin1 <= tbest;
                             const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+#if RT_BRANCHLESS_STEP
+                            // select-based step: one predicated push, one predicated pop, no 4-way branch
+                            const bool swap = tmin1 < tmin0;
+                            const bool take1 = h1 && (!h0 || swap);
+                            if (h0 && h1) stack[sp++] = swap ? c0 : c1;
+                            node = take1 ? c1 : c0;
+                            if (!(h0 || h1)) node = stack[--sp];
+#else
                             if (h0 && h1) {
                                 const bool swap = tmin1 < tmin0;
                                 node = swap ? c1 : c0;
@@ -180,6 +191,7 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
                             } else {
                                 node = stack[--sp];
                             }
+#endif
 #if RT_WHILE_WHILE
                         }
                         if (node < 0) {
@@ -202,7 +214,7 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
                                             break;
                                         }
                                     } else {
-                                        closest_update(p, ray.oct, t, prim, tbest, pbest, tsecond);
+                                        closest_update(p, ray, t, prim, tbest, pbest, tsecond);
                                     }
                                 }
                             }
