@@ -363,7 +363,7 @@ def run_b200(args):
                            "shadow": shadow, "shadow_occluded": occluded, "parallelism": f"tiles32x32_interleaved_x{world}",
                            "gather": "none" if world == 1 else ("fused: kernels store into rank 0's frame over NVLink P2P (CUDA IPC), one barrier" if peer is not None
                                                                else "nccl gather of packed tiles + scatter kernel"),
-                           "l2": "flushed between timed iterations (256 MiB write)", "bvh": {0: "default", 1: "lbvh_gpu", 2: "sah_host", 3: "ploc_gpu"}[info.builder],
+                           "l2": "flushed between timed iterations (256 MiB write)", "bvh": {0: "default", 1: "lbvh_gpu", 2: "sah_host", 3: "ploc_gpu", 4: "auto"}[info.builder],
                            "bvh_nodes": info.bvh_nodes, "scene_build_s": build_s, "frame_sha256": frame_sha},
                 "ms_per_frame": ms_per_step, "render_kernel_ms": kernel_ms, "wall_s_timed_region": wall_s,
                 "step_ms_rank0": [round(x, 3) for x in step_ms],

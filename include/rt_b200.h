@@ -97,10 +97,12 @@ typedef struct RtCamera {
 } RtCamera;
 
 /* acceleration-structure builders (rt_scene_create) */
-#define RT_BUILD_DEFAULT 0 /* = RT_BUILD_PLOC_GPU */
+#define RT_BUILD_DEFAULT 0 /* = RT_BUILD_AUTO */
 #define RT_BUILD_LBVH_GPU 1 /* Morton + radix sort + Karras on the GPU */
 #define RT_BUILD_SAH_HOST 2 /* binned SAH on the host (quality yardstick) */
 #define RT_BUILD_PLOC_GPU 3 /* Morton sort + PLOC agglomerative clustering + SAH leaf collapse on the GPU */
+#define RT_BUILD_AUTO 4     /* PLOC on the GPU and binned SAH on the host; keeps the PLOC tree when its SAH cost is < 0.8x
+                               the host tree's (RtSceneInfo.builder tells which one was kept) */
 
 typedef struct RtBuildOptions {
   int32_t builder;    /* RT_BUILD_* */

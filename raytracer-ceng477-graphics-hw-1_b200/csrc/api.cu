@@ -413,7 +413,7 @@ int rt_scene_create(const RtSceneDesc *desc, const RtBuildOptions *opts, RtScene
     memset(&s->base, 0, sizeof s->base);
     const int nt = desc->n_triangles, ns = desc->n_spheres, np = nt + ns;
     int builder = opts ? opts->builder : RT_BUILD_DEFAULT;
-    if (builder == RT_BUILD_DEFAULT) builder = RT_BUILD_PLOC_GPU;  // best traversal cost of the three on the shipped scenes
+    if (builder == RT_BUILD_DEFAULT) builder = RT_BUILD_AUTO;
 
     const double t0 = now_ms();
     // reference-order tie ranks
@@ -427,13 +427,26 @@ int rt_scene_create(const RtSceneDesc *desc, const RtBuildOptions *opts, RtScene
     HostBvh bvh;
     float ms_device = 0;
     double ms_device_wall = 0;  // includes CUDA context creation on the first call; not host build work
-    if (builder == RT_BUILD_LBVH_GPU || builder == RT_BUILD_PLOC_GPU) {
+    if (builder == RT_BUILD_LBVH_GPU || builder == RT_BUILD_PLOC_GPU || builder == RT_BUILD_AUTO) {
         const double td0 = now_ms();
-        int e = build_bvh_device(bounds, bvh, &ms_device, builder == RT_BUILD_PLOC_GPU);
+        int e = build_bvh_device(bounds, bvh, &ms_device, builder != RT_BUILD_LBVH_GPU);
         ms_device_wall = now_ms() - td0;
         if (e != 0) {
             delete s;
             return fail(RT_ERR_CUDA, "device BVH build failed");
+        }
+        if (builder == RT_BUILD_AUTO) {
+            // AUTO: the GPU-built PLOC tree is kept when its SAH cost is clearly lower than the host binned-SAH
+            // tree's (< 0.8x: scenes with huge primitives next to dense meshes, e.g. horse_and_mug 4.4 vs 7.2);
+            // otherwise the shallower host tree traverses 4-12 % faster (tools/ploc_tune.py).
+            HostBvh host_tree;
+            build_bvh_sah_host(bounds, host_tree);
+            if (tree_depth(bvh) > 60 || !(bvh_sah_cost(bvh) < 0.8f * bvh_sah_cost(host_tree))) {
+                bvh = host_tree;
+                builder = RT_BUILD_SAH_HOST;
+            } else {
+                builder = RT_BUILD_PLOC_GPU;
+            }
         }
     } else {
         build_bvh_sah_host(bounds, bvh);
@@ -450,6 +463,7 @@ int rt_scene_create(const RtSceneDesc *desc, const RtBuildOptions *opts, RtScene
         delete s;
         return fail(RT_ERR_STATE, "BVH deeper than the traversal stack");
     }
+    compact_dfs(bvh);
     const float sah = bvh_sah_cost(bvh);
     pad_boxes(bvh, bounds);
     // A single-primitive scene has a root with one real child.  The missing child becomes a leaf over a dummy

@@ -179,6 +179,32 @@ void pad_boxes(HostBvh &bvh, const std::vector<Aabb> &bounds) {
     }
 }
 
+// Re-lays the reachable nodes out in depth-first order (a node's first child right behind it) and drops the
+// unreachable ones (the GPU builders leave the interior of collapsed subtrees behind): smaller array, and the
+// nodes a ray touches next are the ones next in memory.
+void compact_dfs(HostBvh &bvh) {
+    if (bvh.nodes.empty()) return;
+    std::vector<HostNode> out;
+    out.reserve(bvh.nodes.size());
+    std::vector<std::pair<int, int>> todo;  // (old index, slot in `out` whose child ref must be patched: -1 root, 2k+c)
+    todo.emplace_back(0, -1);
+    while (!todo.empty()) {
+        auto [old_idx, patch] = todo.back();
+        todo.pop_back();
+        const int me = (int) out.size();
+        out.push_back(bvh.nodes[old_idx]);
+        if (patch >= 0) {
+            if (patch & 1) out[patch >> 1].child1 = me;
+            else out[patch >> 1].child0 = me;
+        }
+        const HostNode &n = bvh.nodes[old_idx];
+        // push child1 first so that child0's subtree is emitted right after this node
+        if (n.child1 >= 0 && n.child1 != kEmptyChild) todo.emplace_back(n.child1, 2 * me + 1);
+        if (n.child0 >= 0 && n.child0 != kEmptyChild) todo.emplace_back(n.child0, 2 * me);
+    }
+    bvh.nodes.swap(out);
+}
+
 float bvh_sah_cost(const HostBvh &bvh) {
     if (bvh.nodes.empty()) return 0;
     // root box = union of the root's children

@@ -151,8 +151,8 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
                         }
                     }
                 } else {
-                    int sp = 0;
-                    stack[sp++] = kSentinel;
+                    int *sp = stack;  // pointer, not index: saves the index scaling on every push/pop
+                    *sp++ = kSentinel;
                     int node = 0;
                     while (node != kSentinel) {
 #if RT_WHILE_WHILE
@@ -176,20 +176,20 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
                             // select-based step: one predicated push, one predicated pop, no 4-way branch
                             const bool swap = tmin1 < tmin0;
                             const bool take1 = h1 && (!h0 || swap);
-                            if (h0 && h1) stack[sp++] = swap ? c0 : c1;
+                            if (h0 && h1) *sp++ = swap ? c0 : c1;
                             node = take1 ? c1 : c0;
-                            if (!(h0 || h1)) node = stack[--sp];
+                            if (!(h0 || h1)) node = *--sp;
 #else
                             if (h0 && h1) {
                                 const bool swap = tmin1 < tmin0;
                                 node = swap ? c1 : c0;
-                                stack[sp++] = swap ? c0 : c1;
+                                *sp++ = swap ? c0 : c1;
                             } else if (h0) {
                                 node = c0;
                             } else if (h1) {
                                 node = c1;
                             } else {
-                                node = stack[--sp];
+                                node = *--sp;
                             }
 #endif
 #if RT_WHILE_WHILE
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
 #endif
                             const int enc = ~node;
                             const int first = enc >> 3, count = (enc & 7) + 1;
-                            node = stack[--sp];
+                            node = *--sp;
                             for (int s = first; s < first + count; s++) {
                                 float t;
                                 int prim;
