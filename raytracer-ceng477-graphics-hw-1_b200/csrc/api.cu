@@ -210,6 +210,7 @@ int enqueue_part(RtScene *s, const RtCamera *cam, int aa, int rank, int world, u
     if (P > RT_TILE) P = RT_TILE;
     if (P < 1) P = 1;
     if (s->kernel >= 2) {
+        if (const char *tp = getenv("RT_B200_TILE_P")) P = atoi(tp) > 0 ? atoi(tp) : P;  // experiments only
         if (aa > 1 && P > 16) P = 16;
         // small frames: shrink the warp tile (down to 8 sub-samples a side) until there are enough tiles to
         // give every resident warp a few dozen of them (dynamic load balance: tiles differ a lot in cost)
