@@ -1,4 +1,11 @@
-// render.cu — the per-pixel Whitted hot path as one persistent CUDA kernel for sm_100a.
+// render.cu — the A/B baselines of the render kernel, plus the multi-GPU tile scatter.
+//
+//   render_kernel     (RT_B200_KERNEL=1)  the first shape of the path: a CTA of 256 threads owns a tile, each thread
+//                                         runs whole paths (trace_path), SSAA sums in CTA-shared memory, barriers
+//   render_kernel_v3  (RT_B200_KERNEL=3)  the same per-thread code with warp-granular tiles, no barriers
+// The product default is render_kernel_v2 (render_v2.cu); these two stay selectable because the ncu comparison that
+// motivated it (profiles/r1_kernel_variants_compared.txt) is between the three, and every GPU
+// parity test on seeded scenes runs all of them.
 //
 // Replaces, per sub-sample (reference lines in brackets):
 //   eye ray generation                [raytracer.cpp:319-324]
