@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--width", type=int, default=7680)
     ap.add_argument("--height", type=int, default=3840)
     ap.add_argument("--aa", type=int, default=16)
-    ap.add_argument("--builder", default="default", choices=["default", "sah", "lbvh", "ploc"])
+    ap.add_argument("--builder", default="default", choices=["default", "sah", "lbvh", "ploc", "sah_gpu"])
     ap.add_argument("--cpu-rows", type=int, default=0, help="sub-sample rows in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", default="nccl", choices=["nccl", "p2p"],
@@ -201,7 +201,7 @@ def run_b200(args):
 
     sc = H.golden_scene(args.scene)
     cam = sc.camera(0, args.width, args.height)
-    builder = {"default": 0, "lbvh": 1, "sah": 2, "ploc": 3}[args.builder]
+    builder = {"default": 0, "lbvh": 1, "sah": 2, "ploc": 3, "sah_gpu": 5}[args.builder]
     torch.zeros(1, device="cuda")  # CUDA context up before the scene build is timed
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -363,7 +363,7 @@ def run_b200(args):
                            "shadow": shadow, "shadow_occluded": occluded, "parallelism": f"tiles32x32_interleaved_x{world}",
                            "gather": "none" if world == 1 else ("fused: kernels store into rank 0's frame over NVLink P2P (CUDA IPC), one barrier" if peer is not None
                                                                else "nccl gather of packed tiles + scatter kernel"),
-                           "l2": "flushed between timed iterations (256 MiB write)", "bvh": {0: "default", 1: "lbvh_gpu", 2: "sah_host", 3: "ploc_gpu", 4: "auto"}[info.builder],
+                           "l2": "flushed between timed iterations (256 MiB write)", "bvh": {0: "default", 1: "lbvh_gpu", 2: "sah_host", 3: "ploc_gpu", 4: "auto", 5: "sah_gpu"}[info.builder],
                            "bvh_nodes": info.bvh_nodes, "scene_build_s": build_s, "frame_sha256": frame_sha},
                 "ms_per_frame": ms_per_step, "render_kernel_ms": kernel_ms, "wall_s_timed_region": wall_s,
                 "step_ms_rank0": [round(x, 3) for x in step_ms],

@@ -101,8 +101,9 @@ typedef struct RtCamera {
 #define RT_BUILD_LBVH_GPU 1 /* Morton + radix sort + Karras on the GPU */
 #define RT_BUILD_SAH_HOST 2 /* binned SAH on the host (quality yardstick) */
 #define RT_BUILD_PLOC_GPU 3 /* Morton sort + PLOC agglomerative clustering + SAH leaf collapse on the GPU */
-#define RT_BUILD_AUTO 4     /* PLOC on the GPU and binned SAH on the host; keeps the PLOC tree when its SAH cost is < 0.8x
-                               the host tree's (RtSceneInfo.builder tells which one was kept) */
+#define RT_BUILD_AUTO 4     /* PLOC and top-down binned SAH, both on the GPU; keeps the PLOC tree when its SAH cost is
+                               < 0.8x the other's (RtSceneInfo.builder tells which one was kept) */
+#define RT_BUILD_SAH_GPU 5  /* top-down binned SAH on the GPU (same algorithm as RT_BUILD_SAH_HOST) */
 
 typedef struct RtBuildOptions {
   int32_t builder;    /* RT_BUILD_* */

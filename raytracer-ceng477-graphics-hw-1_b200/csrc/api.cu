@@ -26,6 +26,7 @@ int render_kernel_v2_occupancy(int *ctas_per_sm, int *warps_per_cta);
 int launch_render_v3(const RenderParams &p, int n_ctas, cudaStream_t stream);
 int render_kernel_v3_occupancy(int *ctas_per_sm, int *warps_per_cta);
 int build_bvh_device(const std::vector<Aabb> &bounds, HostBvh &out, float *ms_device, int use_ploc);
+int build_bvh_sah_device(const std::vector<Aabb> &bounds, HostBvh &out, float *ms_device);
 }  // namespace rtb
 
 using namespace rtb;
@@ -437,18 +438,32 @@ int rt_scene_create(const RtSceneDesc *desc, const RtBuildOptions *opts, RtScene
             return fail(RT_ERR_CUDA, "device BVH build failed");
         }
         if (builder == RT_BUILD_AUTO) {
-            // AUTO: the GPU-built PLOC tree is kept when its SAH cost is clearly lower than the host binned-SAH
-            // tree's (< 0.8x: scenes with huge primitives next to dense meshes, e.g. horse_and_mug 4.4 vs 7.2);
-            // otherwise the shallower host tree traverses 4-12 % faster (tools/ploc_tune.py).
-            HostBvh host_tree;
-            build_bvh_sah_host(bounds, host_tree);
-            if (tree_depth(bvh) > 60 || !(bvh_sah_cost(bvh) < 0.8f * bvh_sah_cost(host_tree))) {
-                bvh = host_tree;
-                builder = RT_BUILD_SAH_HOST;
+            // AUTO: both trees are built on the GPU.  The PLOC tree is kept when its SAH cost is clearly lower than
+            // the top-down binned-SAH tree's (< 0.8x: scenes with huge primitives next to dense meshes, e.g.
+            // horse_and_mug 4.4 vs 7.2); otherwise the shallower top-down tree traverses 4-12 % faster
+            // (tools/ploc_tune.py).
+            HostBvh sah_tree;
+            float ms_sah = 0;
+            if (build_bvh_sah_device(bounds, sah_tree, &ms_sah) != 0) {
+                delete s;
+                return fail(RT_ERR_CUDA, "device SAH build failed");
+            }
+            ms_device += ms_sah;
+            if (tree_depth(bvh) > 60 || !(bvh_sah_cost(bvh) < 0.8f * bvh_sah_cost(sah_tree))) {
+                bvh = sah_tree;
+                builder = RT_BUILD_SAH_GPU;
             } else {
                 builder = RT_BUILD_PLOC_GPU;
             }
+            ms_device_wall = now_ms() - td0;
         }
+    } else if (builder == RT_BUILD_SAH_GPU) {
+        const double td0 = now_ms();
+        if (build_bvh_sah_device(bounds, bvh, &ms_device) != 0) {
+            delete s;
+            return fail(RT_ERR_CUDA, "device SAH build failed");
+        }
+        ms_device_wall = now_ms() - td0;
     } else {
         build_bvh_sah_host(bounds, bvh);
     }

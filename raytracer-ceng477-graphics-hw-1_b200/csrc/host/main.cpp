@@ -6,7 +6,7 @@
 // directory and prints the same three timing lines.  The reference fixes its AA factor at compile
 // time (2, raytracer.cpp:26-28); here 2 is the default and `--aa N` selects it at run time.
 //
-//   raytracer scene.xml [--aa N] [--res WxH] [--gpus N] [--builder ploc|lbvh|sah] [--stats]
+//   raytracer scene.xml [--aa N] [--res WxH] [--gpus N] [--builder ploc|sah_gpu|lbvh|sah] [--stats]
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -38,12 +38,12 @@ int main(int argc, char *argv[]) {
             }
         } else if (a == "--builder" && i + 1 < argc) {
             std::string b = argv[++i];
-            builder = b == "lbvh" ? RT_BUILD_LBVH_GPU : b == "sah" ? RT_BUILD_SAH_HOST : b == "ploc" ? RT_BUILD_PLOC_GPU : RT_BUILD_DEFAULT;
+            builder = b == "lbvh" ? RT_BUILD_LBVH_GPU : b == "sah" ? RT_BUILD_SAH_HOST : b == "ploc" ? RT_BUILD_PLOC_GPU : b == "sah_gpu" ? RT_BUILD_SAH_GPU : RT_BUILD_DEFAULT;
         } else if (a == "--stats") want_stats = true;
         else if (!xml) xml = argv[i];
     }
     if (!xml) {
-        fprintf(stderr, "usage: raytracer scene.xml [--aa N] [--res WxH] [--gpus N] [--builder ploc|lbvh|sah] [--stats]\n");
+        fprintf(stderr, "usage: raytracer scene.xml [--aa N] [--res WxH] [--gpus N] [--builder ploc|sah_gpu|lbvh|sah] [--stats]\n");
         return 2;
     }
     try {

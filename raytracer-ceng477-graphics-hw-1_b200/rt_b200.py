@@ -22,7 +22,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 
 RT_TILE = 32
-RT_BUILD_DEFAULT, RT_BUILD_LBVH_GPU, RT_BUILD_SAH_HOST, RT_BUILD_PLOC_GPU, RT_BUILD_AUTO = 0, 1, 2, 3, 4
+RT_BUILD_DEFAULT, RT_BUILD_LBVH_GPU, RT_BUILD_SAH_HOST, RT_BUILD_PLOC_GPU, RT_BUILD_AUTO, RT_BUILD_SAH_GPU = 0, 1, 2, 3, 4, 5
 
 
 class RtVec3(C.Structure):

@@ -96,15 +96,15 @@ def test_oracle_on_odd_configuration():
 
 @pytest.mark.parametrize("key", ["simple.aa1", "cornellbox_front.aa1", "marbles.aa1", "bunny.aa1", "horse_and_mug.aa1",
                                  "dragon_lowres.aa1", "low_poly_scene.aa1", "mirror_spheres.aa1", "Car.aa1"])
-@pytest.mark.parametrize("builder", ["lbvh", "ploc"])
+@pytest.mark.parametrize("builder", ["lbvh", "ploc", "sah_gpu"])
 def test_gpu_bvh_builders(key, builder):
     """The BVHs built on the GPU (Morton + bitonic sort, then Karras' radix tree or PLOC clustering, SAH leaf collapse)
     must give the same frames: the tree is only a filter, ties are settled by the reference-order ranks."""
     gold, m = H.golden_image(key)
     sc = H.golden_scene(m["scene"])
-    rt = tracer(m["scene"], builder={"lbvh": H.rt_b200.RT_BUILD_LBVH_GPU, "ploc": H.rt_b200.RT_BUILD_PLOC_GPU}[builder])
+    rt = tracer(m["scene"], builder={"lbvh": H.rt_b200.RT_BUILD_LBVH_GPU, "ploc": H.rt_b200.RT_BUILD_PLOC_GPU, "sah_gpu": H.rt_b200.RT_BUILD_SAH_GPU}[builder])
     img = rt.render(sc.camera(m["camera"]), 1)
-    inf, ref_inf = rt.info(), tracer(m["scene"]).info()
+    inf, ref_inf = rt.info(), tracer(m["scene"], builder=H.rt_b200.RT_BUILD_SAH_HOST).info()
     print(key, H.diff_report(gold, img), f"{builder}: {inf.bvh_nodes} nodes depth {inf.bvh_max_depth} sah {inf.bvh_sah_cost:.1f} "
           f"build {inf.ms_build_device:.3f} ms device, {rt.last_stats.ms_render:.3f} ms render | sah_host: {ref_inf.bvh_nodes} nodes "
           f"sah {ref_inf.bvh_sah_cost:.1f} build {ref_inf.ms_build_host:.1f} ms host")
@@ -218,7 +218,8 @@ def test_seeded_scenes_against_oracle(seed):
     aa = 1 + seed % 3
     want, ost = H.OracleScene(sc).render(cam, aa)
     import os
-    builders = (H.rt_b200.RT_BUILD_PLOC_GPU, H.rt_b200.RT_BUILD_LBVH_GPU, H.rt_b200.RT_BUILD_SAH_HOST)
+    builders = (H.rt_b200.RT_BUILD_PLOC_GPU, H.rt_b200.RT_BUILD_SAH_GPU, H.rt_b200.RT_BUILD_SAH_HOST) if seed % 2 else \
+        (H.rt_b200.RT_BUILD_LBVH_GPU, H.rt_b200.RT_BUILD_SAH_GPU, H.rt_b200.RT_BUILD_AUTO)
     for kernel, builder in (("2", builders[seed % 3]), ("1", builders[(seed + 1) % 3]), ("3", builders[(seed + 2) % 3])):
         os.environ["RT_B200_KERNEL"] = kernel
         try:
