@@ -221,6 +221,11 @@ int rt_ipc_close(void *d_ptr);
  * visit order): ranks_out[8][n_triangles + n_spheres]; stats4 = nodes, leaves,
  * max leaf size, max depth of the reference's tree. Either may be NULL. */
 int rt_host_reference_ranks(const RtSceneDesc *desc, uint32_t *ranks_out, int32_t *stats4);
+/* FNV-1a hash of the rebuilt reference tree (host build). */
+int rt_host_reference_tree_hash(const RtSceneDesc *desc, uint64_t *hash);
+/* The same ranks, statistics and tree hash from the GPU build that rt_scene_create uses
+ * (needs a device; tests compare it with the host build bit for bit). */
+int rt_device_reference_ranks(const RtSceneDesc *desc, uint32_t *ranks_out, int32_t *stats4, uint64_t *tree_hash);
 /* Builds the host SAH BVH, pads it and checks its invariants (every primitive
  * in exactly one leaf, every box contains what is below it). Returns the node
  * count (>= 0) or a negative error. */

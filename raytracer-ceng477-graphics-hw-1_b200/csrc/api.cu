@@ -27,6 +27,8 @@ int launch_render_v3(const RenderParams &p, int n_ctas, cudaStream_t stream);
 int render_kernel_v3_occupancy(int *ctas_per_sm, int *warps_per_cta);
 int build_bvh_device(const std::vector<Aabb> &bounds, HostBvh &out, float *ms_device, int use_ploc);
 int build_bvh_sah_device(const std::vector<Aabb> &bounds, HostBvh &out, float *ms_device);
+int build_reference_ranks_device(const RtSceneDesc &d, const std::vector<Aabb> &bounds, std::vector<uint32_t> &ranks,
+                                 RefTreeStats &stats, RefTree &tree, float *ms_device);
 }  // namespace rtb
 
 using namespace rtb;
@@ -390,6 +392,51 @@ int rt_host_check_bvh(const RtSceneDesc *desc, float *sah_cost, int32_t *max_dep
     return (int) bvh.nodes.size();
 }
 
+// FNV-1a over the reference tree (boxes, axes, child links, leaf ranges, leaf order): equal hashes <=> equal trees
+static uint64_t ref_tree_hash(const RefTree &t) {
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const void *p, size_t n) {
+        const unsigned char *b = (const unsigned char *) p;
+        for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 1099511628211ull;
+    };
+    for (auto &n: t.nodes) {
+        mix(n.mn, sizeof n.mn);
+        mix(n.mx, sizeof n.mx);
+        const int v[5] = {n.is_leaf ? 0 : n.axis, n.is_leaf, n.is_leaf ? -1 : n.right, n.first, n.count};
+        mix(v, sizeof v);
+    }
+    mix(t.leaf_prims.data(), t.leaf_prims.size() * sizeof(int));
+    mix(t.leaf_of_prim.data(), t.leaf_of_prim.size() * sizeof(int));
+    return h;
+}
+
+int rt_host_reference_tree_hash(const RtSceneDesc *desc, uint64_t *hash) {
+    int rc = validate(desc);
+    if (rc != RT_OK) return rc;
+    std::vector<uint32_t> ranks;
+    RefTreeStats st;
+    RefTree tree;
+    build_reference_ranks(*desc, ranks, st, &tree);
+    *hash = ref_tree_hash(tree);
+    return RT_OK;
+}
+
+// the GPU build of the same tree and ranks (ref_order_device.cu); needs a device
+int rt_device_reference_ranks(const RtSceneDesc *desc, uint32_t *ranks_out, int32_t *stats4, uint64_t *tree_hash) {
+    int rc = validate(desc);
+    if (rc != RT_OK) return rc;
+    std::vector<Aabb> bounds;
+    primitive_bounds(*desc, bounds);
+    std::vector<uint32_t> ranks;
+    RefTreeStats st;
+    RefTree tree;
+    if (build_reference_ranks_device(*desc, bounds, ranks, st, tree, nullptr) != 0) return fail(RT_ERR_CUDA, "device build failed");
+    if (ranks_out) memcpy(ranks_out, ranks.data(), ranks.size() * sizeof(uint32_t));
+    if (stats4) stats4[0] = st.nodes, stats4[1] = st.leaves, stats4[2] = st.max_leaf, stats4[3] = st.max_depth;
+    if (tree_hash) *tree_hash = ref_tree_hash(tree);
+    return RT_OK;
+}
+
 float rt_host_pow_ref(float base, float e) { return pow_ref(base, e); }
 int rt_host_specular_gate(float cos_theta) { return specular_gate(cos_theta) ? 1 : 0; }
 
@@ -422,9 +469,20 @@ int rt_scene_create(const RtSceneDesc *desc, const RtBuildOptions *opts, RtScene
     std::vector<uint32_t> ranks;
     RefTreeStats rstats;
     RefTree rtree;
-    build_reference_ranks(*desc, ranks, rstats, &rtree);
     std::vector<Aabb> bounds;
     primitive_bounds(*desc, bounds);
+    float ms_ranks_device = 0;
+    double ms_ranks_wall = 0;
+    if (getenv("RT_B200_HOST_RANKS")) {  // the host implementation (ref_order.cpp) stays as the cross-check
+        build_reference_ranks(*desc, ranks, rstats, &rtree);
+    } else {
+        const double tr0 = now_ms();
+        if (build_reference_ranks_device(*desc, bounds, ranks, rstats, rtree, &ms_ranks_device) != 0) {
+            delete s;
+            return fail(RT_ERR_CUDA, "device build of the reference-order tree failed");
+        }
+        ms_ranks_wall = now_ms() - tr0;
+    }
 
     HostBvh bvh;
     float ms_device = 0;
@@ -669,8 +727,8 @@ int rt_scene_create(const RtSceneDesc *desc, const RtBuildOptions *opts, RtScene
     inf.ref_tree_leaves = rstats.leaves;
     inf.ref_tree_max_leaf = rstats.max_leaf;
     inf.ref_tree_max_depth = rstats.max_depth;
-    inf.ms_build_host = (float) (t1 - t0 - ms_device_wall);
-    inf.ms_build_device = ms_device;
+    inf.ms_build_host = (float) (t1 - t0 - ms_device_wall - ms_ranks_wall);
+    inf.ms_build_device = ms_device + ms_ranks_device;
     inf.bvh_sah_cost = sah;
     inf.builder = builder;
     inf.device = dev;

@@ -274,3 +274,27 @@ def test_argument_errors():
     with pytest.raises(H.rt_b200.RtError, match="aa_factor"):
         rt.render(rt.scene.camera(0), 0)
     rt.close()
+
+
+@pytest.mark.parametrize("scene", sorted(H.manifest()["scenes"]))
+def test_reference_tree_on_gpu_equals_host(scene):
+    """The reference-order tree and the 8 rank arrays built on the GPU (ref_order_device.cu, what rt_scene_create
+    uses) against the host build (ref_order.cpp), whose statistics equal the reference's own builder's: ranks, node /
+    leaf / depth statistics and an FNV hash over every node box, link and leaf list must be identical."""
+    import ctypes as C
+    L = H.rt_b200.cuda_lib()
+    L.rt_host_reference_ranks.argtypes = [C.POINTER(H.RtSceneDesc), C.c_void_p, C.c_void_p]
+    L.rt_host_reference_tree_hash.argtypes = [C.POINTER(H.RtSceneDesc), C.POINTER(C.c_uint64)]
+    L.rt_device_reference_ranks.argtypes = [C.POINTER(H.RtSceneDesc), C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+    sc = H.golden_scene(scene)
+    n = sc.desc.n_triangles + sc.desc.n_spheres
+    hr, dr = np.zeros((8, n), np.uint32), np.zeros((8, n), np.uint32)
+    hs, ds = (C.c_int32 * 4)(), (C.c_int32 * 4)()
+    hh, dh = C.c_uint64(), C.c_uint64()
+    assert L.rt_host_reference_ranks(C.byref(sc.desc), hr.ctypes.data, hs) == 0
+    assert L.rt_host_reference_tree_hash(C.byref(sc.desc), C.byref(hh)) == 0
+    assert L.rt_device_reference_ranks(C.byref(sc.desc), dr.ctypes.data, ds, C.byref(dh)) == 0, L.rt_last_error()
+    assert list(hs) == list(ds)
+    assert dict(zip(["nodes", "leaves", "max_leaf", "max_depth"], list(ds))) == H.manifest()["scenes"][scene]["ref_bvh"]
+    assert np.array_equal(hr, dr)
+    assert hh.value == dh.value
