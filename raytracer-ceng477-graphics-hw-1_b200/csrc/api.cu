@@ -225,13 +225,24 @@ int enqueue_part(RtScene *s, const RtCamera *cam, int aa, int rank, int world, u
             P = (P + 1) / 2;
         }
     }
+    int Ph = P;
+    if (s->kernel >= 2 && P * aa == 8 && 4 % aa == 0) {
+        // still too few tiles for the machine (a 1440x720 frame without AA has 16 K tiles of 64 pixels for 4144
+        // resident warps): halve the tile once more to a single 8x4 round of sub-samples
+        const long long slots = s->kernel == 2 ? (long long) s->n_sms * s->ctas_per_sm2 * s->warps_per_cta2
+                                               : (long long) s->n_sms * s->ctas_per_sm3 * s->warps_per_cta3;
+        const long long ix = (RT_TILE + P - 1) / P;
+        if (part_tiles(g, rank, world) * ix * ix < 32 * slots) Ph = 4 / aa;
+    }
     p.P = P;
+    p.Ph = Ph;
     p.items_x = (RT_TILE + P - 1) / P;
+    p.items_y = (RT_TILE + Ph - 1) / Ph;
     p.tiles_x = g.tiles_x;
     p.tiles_y = g.tiles_y;
     p.part_rank = rank;
     p.part_world = world;
-    const long long n_items = part_tiles(g, rank, world) * (long long) p.items_x * p.items_x;
+    const long long n_items = part_tiles(g, rank, world) * (long long) p.items_x * p.items_y;
     if (n_items >= (1LL << 32) - (1 << 22)) return fail(RT_ERR_INVALID, "too many work items");
     p.n_items = (unsigned) n_items;
     p.out_mode = out_mode;

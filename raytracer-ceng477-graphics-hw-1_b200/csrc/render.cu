@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(kThreads3, RT_MIN_CTAS3) render_kernel_v3(cons
     const int lane = threadIdx.x & 31;
     unsigned *acc = acc_all[threadIdx.x >> 5];
     const int f = p.f, P = p.P;
-    const int items_per_tile = p.items_x * p.items_x;
+    const int items_per_tile = p.items_x * p.items_y;
     const bool warp_in_one_pixel = (f % 8) == 0;
     Counters cnt = {0u, 0u, 0u, 0u, 0u, 0u};
     const V3 E0 = ld3(p.e), Q = ld3(p.q), U = ld3(p.u), Vv = ld3(p.v);
@@ -360,10 +360,10 @@ __global__ void __launch_bounds__(kThreads3, RT_MIN_CTAS3) render_kernel_v3(cons
         const int sub = (int) (item % (unsigned) items_per_tile);
         const int tile = p.part_rank + local_tile * p.part_world;
         const int tx0 = (tile % p.tiles_x) * RT_TILE, ty0 = (tile / p.tiles_x) * RT_TILE;
-        const int ix0 = (sub % p.items_x) * P, iy0 = (sub / p.items_x) * P;
+        const int ix0 = (sub % p.items_x) * P, iy0 = (sub / p.items_x) * p.Ph;
         const int px0 = tx0 + ix0, py0 = ty0 + iy0;
         const int pw = max(0, min(min(P, RT_TILE - ix0), p.nx - px0));
-        const int ph = max(0, min(min(P, RT_TILE - iy0), p.ny - py0));
+        const int ph = max(0, min(min(p.Ph, RT_TILE - iy0), p.ny - py0));
         if (pw == 0 || ph == 0) continue;
         const int sw = pw * f, sh = ph * f;
         const int nbx = (sw + 7) >> 3, nby = (sh + 3) >> 2;

@@ -41,7 +41,9 @@ struct RenderParams {
     int nx, ny;          // output resolution
     int f;               // supersampling factor (sub-sample grid is nx*f by ny*f)
     int P;               // output pixels per work-item side
-    int items_x;         // work items per tile side = ceil(RT_TILE / P)
+    int Ph;              // work-item height in pixels (= P except on small frames: one 8x4 round per item)
+    int items_x;         // work items per tile row = ceil(RT_TILE / P)
+    int items_y;         // work items per tile column = ceil(RT_TILE / Ph)
     int tiles_x, tiles_y;
     int part_rank, part_world;
     unsigned int n_items;  // work items of this part

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
     const unsigned lt_mask = (1u << lane) - 1u;
     const int f = p.f, P = p.P;
     unsigned *acc = acc_all + (threadIdx.x >> 5) * (P * P * 3);
-    const int items_per_tile = p.items_x * p.items_x;
+    const int items_per_tile = p.items_x * p.items_y;
     const V3 E0 = ld3(p.e), Q = ld3(p.q), U = ld3(p.u), Vv = ld3(p.v);
     const V3 Ia = ld3(p.ambient);
     Counters cnt = {0u, 0u, 0u, 0u, 0u, 0u};
@@ -72,10 +72,10 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
         const int sub = (int) (item % (unsigned) items_per_tile);
         const int tile = p.part_rank + local_tile * p.part_world;
         const int tx0 = (tile % p.tiles_x) * RT_TILE, ty0 = (tile / p.tiles_x) * RT_TILE;
-        const int ix0 = (sub % p.items_x) * P, iy0 = (sub / p.items_x) * P;
+        const int ix0 = (sub % p.items_x) * P, iy0 = (sub / p.items_x) * p.Ph;
         const int px0 = tx0 + ix0, py0 = ty0 + iy0;
         const int pw = max(0, min(min(P, RT_TILE - ix0), p.nx - px0));
-        const int ph = max(0, min(min(P, RT_TILE - iy0), p.ny - py0));
+        const int ph = max(0, min(min(p.Ph, RT_TILE - iy0), p.ny - py0));
         if (pw == 0 || ph == 0) continue;
         const int sw = pw * f, sh = ph * f;
         const int nbx = (sw + 7) >> 3, nby = (sh + 3) >> 2;
