@@ -298,3 +298,40 @@ def test_reference_tree_on_gpu_equals_host(scene):
     assert dict(zip(["nodes", "leaves", "max_leaf", "max_depth"], list(ds))) == H.manifest()["scenes"][scene]["ref_bvh"]
     assert np.array_equal(hr, dr)
     assert hh.value == dh.value
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("scene,w,h,aa", [("dragon_lowres", 2400, 2400, 3), ("mirror_spheres", 3072, 3072, 2), ("marbles", 1024, 1024, 3),
+                                          ("car", 2048, 1536, 2), ("berserker", 1536, 2048, 2)])
+def test_large_frames_against_oracle(scene, w, h, aa):
+    """BASELINE.json config 4 ("high-triangle and deep-recursion path") and friends at sizes nobody pre-rendered:
+    the GPU frame against the oracle rendered on the box's host cores (a few seconds each) — byte identity and
+    equal ray counts, tens to hundreds of millions of rays per case."""
+    sc = H.golden_scene(scene)
+    cam = sc.camera(0, w, h)
+    want, ost = H.OracleScene(sc).render(cam, aa)
+    rt = tracer(scene)
+    got = rt.render(cam, aa)
+    st = rt.last_stats
+    rep = H.diff_report(want, got)
+    print(scene, rep, "rays", st.total_rays, "replayed", st.replayed_closest, st.replayed_any, f"{st.ms_render:.2f} ms")
+    assert rep["equal"] == rep["pixels"], rep
+    assert (st.primary_rays, st.reflection_rays, st.shadow_rays, st.shadow_occluded) == \
+        (ost.primary_rays, ost.reflection_rays, ost.shadow_rays, ost.shadow_occluded)
+
+
+@pytest.mark.parametrize("scene,cam_idx,w,h,aa", [("cornellbox", 0, 101, 101, 1), ("cornellbox", 2, 51, 51, 3), ("simple", 0, 33, 33, 1),
+                                                  ("mirror_spheres", 0, 65, 65, 1), ("simple_reflectance", 0, 9, 9, 5)])
+def test_axis_parallel_rays(scene, cam_idx, w, h, aa):
+    """Odd resolutions on symmetric near planes put pixel centres exactly on the optical axis: direction components
+    that are exactly 0 (1/d = inf), rays inside the planes of zero-thickness boxes.  The fast box test clamps the
+    reciprocal, the replay uses the reference's inf/NaN arithmetic — both must agree with the oracle."""
+    sc = H.golden_scene(scene)
+    cam = sc.camera(cam_idx, w, h)
+    want, ost = H.OracleScene(sc).render(cam, aa)
+    rt = tracer(scene)
+    got = rt.render(cam, aa)
+    st = rt.last_stats
+    assert np.array_equal(want, got), H.diff_report(want, got)
+    assert (st.primary_rays, st.reflection_rays, st.shadow_rays, st.shadow_occluded) == \
+        (ost.primary_rays, ost.reflection_rays, ost.shadow_rays, ost.shadow_occluded)
