@@ -548,7 +548,7 @@ int rt_scene_create(const RtSceneDesc *desc, const RtBuildOptions *opts, RtScene
         delete s;
         return fail(RT_ERR_STATE, "BVH deeper than the traversal stack");
     }
-    compact_dfs(bvh);
+    compact_dfs(bvh, getenv("RT_B200_BFS_TOP") ? atoi(getenv("RT_B200_BFS_TOP")) : 0);
     const float sah = bvh_sah_cost(bvh);
     pad_boxes(bvh, bounds);
     // A single-primitive scene has a root with one real child.  The missing child becomes a leaf over a dummy

@@ -182,21 +182,36 @@ void pad_boxes(HostBvh &bvh, const std::vector<Aabb> &bounds) {
 // Re-lays the reachable nodes out in depth-first order (a node's first child right behind it) and drops the
 // unreachable ones (the GPU builders leave the interior of collapsed subtrees behind): smaller array, and the
 // nodes a ray touches next are the ones next in memory.
-void compact_dfs(HostBvh &bvh) {
+void compact_dfs(HostBvh &bvh, int bfs_top) {
     if (bvh.nodes.empty()) return;
     std::vector<HostNode> out;
     out.reserve(bvh.nodes.size());
-    std::vector<std::pair<int, int>> todo;  // (old index, slot in `out` whose child ref must be patched: -1 root, 2k+c)
-    todo.emplace_back(0, -1);
-    while (!todo.empty()) {
-        auto [old_idx, patch] = todo.back();
-        todo.pop_back();
+    // (old index, slot in `out` whose child ref must be patched: -1 root, 2k+c)
+    std::vector<std::pair<int, int>> todo;
+    auto emit = [&](int old_idx, int patch) {
         const int me = (int) out.size();
         out.push_back(bvh.nodes[old_idx]);
         if (patch >= 0) {
             if (patch & 1) out[patch >> 1].child1 = me;
             else out[patch >> 1].child0 = me;
         }
+        return me;
+    };
+    // optional breadth-first prefix (the top of the tree in the first `bfs_top` slots: shared-memory experiment)
+    std::vector<std::pair<int, int>> queue(1, {0, -1});
+    size_t head = 0;
+    while (head < queue.size() && (int) out.size() < bfs_top) {
+        auto [old_idx, patch] = queue[head++];
+        const int me = emit(old_idx, patch);
+        const HostNode &n = bvh.nodes[old_idx];
+        if (n.child0 >= 0 && n.child0 != kEmptyChild) queue.emplace_back(n.child0, 2 * me);
+        if (n.child1 >= 0 && n.child1 != kEmptyChild) queue.emplace_back(n.child1, 2 * me + 1);
+    }
+    for (size_t i = queue.size(); i-- > head;) todo.push_back(queue[i]);  // remaining subtrees, depth-first, in order
+    while (!todo.empty()) {
+        auto [old_idx, patch] = todo.back();
+        todo.pop_back();
+        const int me = emit(old_idx, patch);
         const HostNode &n = bvh.nodes[old_idx];
         // push child1 first so that child0's subtree is emitted right after this node
         if (n.child1 >= 0 && n.child1 != kEmptyChild) todo.emplace_back(n.child1, 2 * me + 1);

@@ -28,6 +28,9 @@ constexpr int kMaxP2 = 16;  // warp tile side in pixels when f > 1 (acc size); f
 #ifndef RT_MIN_CTAS2
 #define RT_MIN_CTAS2 7
 #endif
+#ifndef RT_SMEM_TOP
+#define RT_SMEM_TOP 0  // experiment: keep the first RT_SMEM_TOP nodes (breadth-first top of the tree) in shared memory
+#endif
 #ifndef RT_BRANCHLESS_STEP
 #define RT_BRANCHLESS_STEP 1
 #endif
@@ -47,6 +50,11 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
     // warp-private SSAA accumulators, sized per launch (P*P*3 words per warp; nothing when f == 1): whatever shared
     // memory the kernel does not need stays L1 cache for the BVH
     extern __shared__ unsigned acc_all[];
+#if RT_SMEM_TOP
+    __shared__ float4 s_top[4 * RT_SMEM_TOP];
+    for (int i = threadIdx.x; i < 4 * min(RT_SMEM_TOP, p.n_nodes); i += kThreads2) s_top[i] = __ldg(&p.nodes[i]);
+    __syncthreads();
+#endif
 
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -162,10 +170,20 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
 #else
                         if (node >= 0) {
 #endif
+#if RT_SMEM_TOP
+                            float4 n0, n1, n2, n3;
+                            if (node < RT_SMEM_TOP) {
+                                n0 = s_top[4 * node], n1 = s_top[4 * node + 1], n2 = s_top[4 * node + 2], n3 = s_top[4 * node + 3];
+                            } else {
+                                n0 = __ldg(&p.nodes[4 * node]), n1 = __ldg(&p.nodes[4 * node + 1]);
+                                n2 = __ldg(&p.nodes[4 * node + 2]), n3 = __ldg(&p.nodes[4 * node + 3]);
+                            }
+#else
                             const float4 n0 = __ldg(&p.nodes[4 * node]);
                             const float4 n1 = __ldg(&p.nodes[4 * node + 1]);
                             const float4 n2 = __ldg(&p.nodes[4 * node + 2]);
                             const float4 n3 = __ldg(&p.nodes[4 * node + 3]);
+#endif
                             float tmin0, tmax0, tmin1, tmax1;
                             slab(ray, n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, tmin0, tmax0);
                             slab(ray, n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, tmin1, tmax1);

@@ -92,6 +92,6 @@ void build_bvh_sah_host(const std::vector<Aabb> &bounds, HostBvh &out);
 void pad_boxes(HostBvh &bvh, const std::vector<Aabb> &bounds);
 
 float bvh_sah_cost(const HostBvh &bvh);
-void compact_dfs(HostBvh &bvh);
+void compact_dfs(HostBvh &bvh, int bfs_top = 0);
 
 }  // namespace rtb
