@@ -359,6 +359,7 @@ int rt_host_check_bvh(const RtSceneDesc *desc, float *sah_cost, int32_t *max_dep
     build_bvh_sah_host(bounds, bvh);
     if (sah_cost) *sah_cost = bvh_sah_cost(bvh);
     if (max_depth) *max_depth = tree_depth(bvh);
+    compact_dfs(bvh, 7);  // the layout pass every tree goes through (here with a breadth-first prefix) must keep the tree intact
     pad_boxes(bvh, bounds);
     const int np = (int) bounds.size();
     std::vector<int> seen((size_t) np, 0);
