@@ -40,6 +40,10 @@ int main(int argc, char *argv[]) {
             std::string b = argv[++i];
             builder = b == "lbvh" ? RT_BUILD_LBVH_GPU : b == "sah" ? RT_BUILD_SAH_HOST : b == "ploc" ? RT_BUILD_PLOC_GPU : b == "sah_gpu" ? RT_BUILD_SAH_GPU : RT_BUILD_DEFAULT;
         } else if (a == "--stats") want_stats = true;
+        else if (a == "--help" || a == "-h") {
+            xml = nullptr;
+            break;
+        }
         else if (!xml) xml = argv[i];
     }
     if (!xml) {
