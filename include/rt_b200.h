@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 1
+#define RT_B200_ABI_VERSION 2
 
 /* error codes (0 = success, negative = failure; text via rt_last_error()) */
 #define RT_OK 0
@@ -110,7 +110,13 @@ typedef struct RtBuildOptions {
   int32_t brute_force; /* 1: ignore the BVH and test every primitive (parity debugging) */
   int32_t no_exact_culling; /* 1: skip the reference-visibility check (a hit the reference's own box test would
                                have culled is then reported; a few rays per 10^8 on the shipped scenes) */
-  int32_t reserved[5];
+  int32_t refill_threshold; /* experiments: refill idle lanes of a warp once at most this many are busy (0 = default:
+                               only when the warp has drained; needs an AA factor that is not a multiple of 8) */
+  int32_t ploc_radius;      /* experiments: PLOC neighbour search radius (0 = default 16) */
+  float ploc_leaf_cost;     /* experiments: per-primitive cost in PLOC's leaf-collapse decision (0 = default 1.0) */
+  int32_t force_replay;     /* tests: every ray that reports a hit is re-decided by the exact replay of the reference's
+                               traversal (slow; must give the same frame as the default path) */
+  int32_t reserved[1];
 } RtBuildOptions;
 
 /* counters are exact (device atomics); "ray" = one closest-hit query
@@ -137,12 +143,13 @@ typedef struct RtSceneInfo {
   int32_t ref_tree_leaves;
   int32_t ref_tree_max_leaf;
   int32_t ref_tree_max_depth;
-  float ms_build_host;   /* reference-order ranks + host staging */
-  float ms_build_device; /* device BVH build (CUDA events) */
+  float ms_build_host;   /* host time until the whole build was enqueued (validation, uploads, launches) */
+  float ms_build_device; /* uploads + every build kernel on the device (CUDA events) */
   float bvh_sah_cost;
-  int32_t builder;
+  int32_t builder;       /* the builder whose tree was kept (RT_BUILD_AUTO reports PLOC or SAH_GPU) */
   int32_t device;
-  int32_t reserved[3];
+  float sah_cost_ploc, sah_cost_sah; /* RT_BUILD_AUTO: the two candidates' SAH costs (computed on the device) */
+  float ms_create_wall;  /* wall time of the whole rt_scene_create call */
 } RtSceneInfo;
 
 typedef struct RtScene RtScene; /* opaque */
@@ -163,25 +170,39 @@ int rt_scene_info(const RtScene *scene, RtSceneInfo *info);
 int rt_render(RtScene *scene, const RtCamera *cam, int aa_factor, unsigned char *rgb_out,
               RtStats *stats);
 
-/* ---- multi-GPU: interleaved tiles, scene replicated per GPU ---------------
- * The output image is cut into RT_TILE x RT_TILE pixel tiles, numbered
- * row-major; tile k belongs to part (k % part_world).  This mirrors the
- * reference's interleaved rows (raytracer.cpp:353) for load balance.  When
- * the number of tile columns is a multiple of part_world, the numbering uses
- * one extra (empty) phantom column so that a part's tiles run diagonally
- * instead of in fixed vertical stripes. */
-#define RT_TILE 32
+/* Asynchronous variant for rendering several cameras back to back on one resident scene
+ * (raytracer.cpp:505-519): rt_render_async enqueues the frame and returns a ticket; rt_wait blocks until that
+ * frame is in rgb_out.  Up to 3 frames may be in flight per handle; the device-to-host copy of frame i runs on
+ * a second stream while the kernel of frame i+1 executes.  rgb_out must stay valid until rt_wait; page-locked
+ * memory (rt_host_alloc) avoids a staging copy. */
+int rt_render_async(RtScene *scene, const RtCamera *cam, int aa_factor, unsigned char *rgb_out, int *ticket);
+int rt_wait(RtScene *scene, int ticket, RtStats *stats);
 
-/* number of tiles part `part_rank` owns, and bytes of its packed tile buffer
- * (n_tiles * RT_TILE * RT_TILE * 3; edge tiles are padded). */
-int64_t rt_part_tiles(const RtCamera *cam, int part_rank, int part_world);
-int64_t rt_part_bytes(const RtCamera *cam, int part_rank, int part_world);
+/* Page-locked host memory for frames (cudaMallocHost / cudaFreeHost). */
+int rt_host_alloc(int64_t bytes, void **ptr);
+int rt_host_free(void *ptr);
 
-/* Renders only this part's tiles into DEVICE memory d_tiles (packed, tile-major,
- * rt_part_bytes long) on `cuda_stream` (a cudaStream_t, may be NULL for the
+/* Creates the CUDA context of `device` and loads the render kernels; callable from a helper thread so that both
+ * overlap the caller's scene parsing. */
+int rt_warmup(int device);
+
+/* ---- multi-GPU: interleaved row bands, scene replicated per GPU -----------
+ * The output image is cut into bands of rt_band_height(cam, aa, world) pixel rows; band b belongs to part
+ * (b % part_world).  This mirrors the reference's interleaved rows (raytracer.cpp:353: row i goes to thread
+ * i % cores) for load balance; at the 16x16 headline configuration a band is ONE pixel row.  The band height is a
+ * pure function of (camera, aa_factor, part_world), so every rank and the gathering side agree without talking. */
+int rt_band_height(const RtCamera *cam, int aa_factor, int part_world);
+
+/* pixel rows part `part_rank` owns (its last band padded to the full band height), and bytes of its packed buffer
+ * (rows * image_width * 3). */
+int64_t rt_part_rows(const RtCamera *cam, int aa_factor, int part_rank, int part_world);
+int64_t rt_part_bytes(const RtCamera *cam, int aa_factor, int part_rank, int part_world);
+
+/* Renders only this part's bands into DEVICE memory d_rows (packed: the part's bands back to back,
+ * [local_band][band_h][image_width][3], rt_part_bytes long) on `cuda_stream` (a cudaStream_t, may be NULL for the
  * default stream).  Asynchronous w.r.t. the host unless stats != NULL. */
 int rt_render_part(RtScene *scene, const RtCamera *cam, int aa_factor, int part_rank,
-                   int part_world, void *d_tiles, void *cuda_stream, RtStats *stats);
+                   int part_world, void *d_rows, void *cuda_stream, RtStats *stats);
 
 /* As rt_render_part, but each finished pixel is stored straight into a
  * row-major RGB8 frame at d_frame (image_height*image_width*3 bytes), which
@@ -190,15 +211,28 @@ int rt_render_part(RtScene *scene, const RtCamera *cam, int aa_factor, int part_
 int rt_render_part_into_frame(RtScene *scene, const RtCamera *cam, int aa_factor, int part_rank,
                               int part_world, void *d_frame, void *cuda_stream, RtStats *stats);
 
-/* On the gathering GPU: scatters `part_world` packed tile buffers laid out back
+/* On the gathering GPU: scatters `part_world` packed band buffers laid out back
  * to back with stride `part_stride_bytes` (>= the largest rt_part_bytes) into a
  * row-major RGB8 frame d_frame. */
-int rt_assemble_tiles(const RtCamera *cam, int part_world, const void *d_parts,
+int rt_assemble_parts(const RtCamera *cam, int aa_factor, int part_world, const void *d_parts,
                       int64_t part_stride_bytes, void *d_frame, void *cuda_stream);
 
-/* Single-process multi-GPU convenience used by the `raytracer` CLI: one handle
- * per device in scenes[0..n_gpus), tiles gathered to scenes[0]'s device with
- * peer copies, one D2H. */
+/* End to end without a gather: renders this part's bands and copies them device-to-host over THIS GPU's own PCIe
+ * link straight into their rows of `host_frame` (row-major RGB8, image_height*image_width*3 bytes; one strided
+ * copy).  Synchronous.  With one process per GPU, host_frame is a frame shared by all ranks (rt_host_frame_*);
+ * when every rank has returned, the frame is complete. */
+int rt_render_part_to_host(RtScene *scene, const RtCamera *cam, int aa_factor, int part_rank, int part_world,
+                           unsigned char *host_frame, RtStats *stats);
+
+/* A host frame shared between the processes of one node: POSIX shared memory `name` ("/something"), mapped and
+ * page-locked in the calling process.  One rank creates, the others open; close unmaps (and unlinks when
+ * unlink_name != NULL). */
+int rt_host_frame_create(const char *name, int64_t bytes, void **ptr);
+int rt_host_frame_open(const char *name, int64_t bytes, void **ptr);
+int rt_host_frame_close(void *ptr, int64_t bytes, const char *unlink_name);
+
+/* Single-process multi-GPU (the `raytracer --gpus N` path): one handle per device in scenes[0..n_gpus); every GPU
+ * renders its bands and copies them over its own PCIe link into rgb_out (directly when rgb_out is page-locked). */
 int rt_render_multi(RtScene *const *scenes, int n_gpus, const RtCamera *cam, int aa_factor,
                     unsigned char *rgb_out, RtStats *stats);
 
@@ -234,6 +268,11 @@ int rt_host_check_bvh(const RtSceneDesc *desc, float *sah_cost, int32_t *max_dep
  * (raytracer.cpp:411-414), compiled for the host. */
 float rt_host_pow_ref(float base, float exponent);
 int rt_host_specular_gate(float cos_theta);
+
+/* Device self check (needs a GPU): the kernels' shared-reciprocal division against the IEEE `/` operator on n
+ * pseudo-random operand quadruples, bit for bit; reports the number of mismatches (must be 0) and how many
+ * quadruples took the fast path. */
+int rt_selftest_div3(uint64_t n, uint32_t seed, uint64_t *mismatches, uint64_t *fast_path);
 
 const char *rt_last_error(void);
 int rt_abi_version(void);

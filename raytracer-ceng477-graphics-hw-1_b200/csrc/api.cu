@@ -1,13 +1,18 @@
 // api.cu — the C-ABI of include/rt_b200.h over the CUDA kernels.  No CPU fallback: without a
 // usable GPU every compute entry point fails with RT_ERR_CUDA.
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
-#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <cuda_runtime.h>
 
@@ -15,50 +20,55 @@
 #include "render_params.h"
 #include "rt_b200.h"
 #include "rt_internal.h"
+#include "scene_build.h"
 
 namespace rtb {
-int launch_render(const RenderParams &p, int n_ctas, cudaStream_t stream);
-int launch_assemble(const unsigned char *parts, long long part_stride, int part_world, int nx, int ny, int tiles_x,
-                    int n_tiles, unsigned char *frame, cudaStream_t stream);
-int render_kernel_occupancy(int *ctas_per_sm);
+int launch_assemble(const unsigned char *parts, long long part_stride, int part_world, int nx, int ny, int band_h,
+                    unsigned char *frame, cudaStream_t stream);
 int launch_render_v2(const RenderParams &p, int n_ctas, cudaStream_t stream);
 int render_kernel_v2_occupancy(int *ctas_per_sm, int *warps_per_cta);
-int launch_render_v3(const RenderParams &p, int n_ctas, cudaStream_t stream);
-int render_kernel_v3_occupancy(int *ctas_per_sm, int *warps_per_cta);
-int build_bvh_device(const std::vector<Aabb> &bounds, HostBvh &out, float *ms_device, int use_ploc);
-int build_bvh_sah_device(const std::vector<Aabb> &bounds, HostBvh &out, float *ms_device);
-int build_reference_ranks_device(const RtSceneDesc &d, const std::vector<Aabb> &bounds, std::vector<uint32_t> &ranks,
-                                 RefTreeStats &stats, RefTree &tree, float *ms_device);
 }  // namespace rtb
 
 using namespace rtb;
 
+namespace {
+
+// one frame in flight on a scene handle (rt_render_async double-buffers; rt_render uses the next free slot)
+struct RenderSlot {
+    cudaEvent_t ev_start = nullptr, ev_kernel = nullptr, ev_done = nullptr;
+    unsigned char *d_frame = nullptr;  // grows on demand
+    size_t frame_cap = 0;
+    unsigned char *h_pinned = nullptr;  // staging for D2H into pageable caller memory
+    size_t pinned_cap = 0;
+    unsigned long long *h_stats = nullptr;  // pinned, 8 words
+    // pending frame
+    bool busy = false;
+    unsigned char *dst = nullptr;
+    size_t bytes = 0;
+    bool staged = false;
+    int launches = 0;
+};
+
+constexpr int kFrameSlots = kControlSlots - 1;  // the last control slot belongs to the part calls
+
+}  // namespace
+
 struct RtScene {
     int device = 0;
     int n_sms = 0;
-    int ctas_per_sm = 1;
-    int kernel = 2;  // 1: CTA-tile megakernel (render.cu), 2: warp-tile state machine (render_v2.cu); env RT_B200_KERNEL
-    int ctas_per_sm2 = 1, warps_per_cta2 = 4;
-    int refill_threshold = 0;  // env RT_B200_REFILL
-    int ctas_per_sm3 = 1, warps_per_cta3 = 4;
-    // device buffers
-    float4 *d_tri_nn = nullptr;
-    float4 *d_nodes = nullptr, *d_prims = nullptr, *d_tri_nm = nullptr, *d_sph_cr = nullptr, *d_materials = nullptr,
-           *d_lights = nullptr;
-    int *d_sph_mat = nullptr;
-    uint32_t *d_ranks = nullptr;
-    float4 *d_ref_nodes = nullptr, *d_prim_bounds = nullptr;
-    int *d_ref_leaf_prims = nullptr, *d_slot_of_prim = nullptr;
-    unsigned int *d_counter = nullptr;
-    unsigned long long *d_stats = nullptr;
-    unsigned char *d_frame = nullptr;  // grows on demand
-    size_t frame_cap = 0;
-    unsigned char *d_parts = nullptr;  // rt_render_multi gather buffer on the root device
+    int ctas_per_sm[2] = {1, 1};  // shared-accumulator / register-accumulator instantiation
+    int warps_per_cta = 4;
+    int refill_threshold = 0;
+    void *arena = nullptr;
+    SceneBuffers buf;
+    RenderSlot slot[kFrameSlots];
+    unsigned next_ticket = 0;
+    unsigned char *d_parts = nullptr;  // rt_render_multi / rt_render_part_to_host: this device's packed bands
     size_t parts_cap = 0;
-    unsigned char *h_pinned = nullptr;  // staging for D2H into pageable caller memory
-    size_t pinned_cap = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_part[2] = {nullptr, nullptr};
+    float scene_center[3] = {0, 0, 0};
+    float scene_reach = 0;  // scene diagonal + largest |coordinate|
     // scene constants
     RenderParams base;
     RtSceneInfo info;
@@ -80,13 +90,23 @@ int fail(int code, const std::string &msg) {
             return fail(RT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                           \
     } while (0)
 
-template <typename T>
-int upload(T **dst, const void *src, size_t count) {
-    size_t bytes = sizeof(T) * (count ? count : 1);
-    CU(cudaMalloc((void **) dst, bytes));
-    if (count) CU(cudaMemcpy(*dst, src, sizeof(T) * count, cudaMemcpyHostToDevice));
-    return RT_OK;
-}
+// switches the current device and restores the caller's on every exit path
+struct DeviceGuard {
+    int prev = -1, cur = -1;
+    DeviceGuard() {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        cur = prev;
+    }
+    int use(int dev) {
+        if (dev == cur) return 0;
+        if (cudaSetDevice(dev) != cudaSuccess) return -1;
+        cur = dev;
+        return 0;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
 
 double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -112,7 +132,7 @@ int validate(const RtSceneDesc *d) {
         if (!vid(d->spheres[i].center_vertex_id)) return fail(RT_ERR_INVALID, "sphere centre id out of range");
         if (!mid(d->spheres[i].material_id)) return fail(RT_ERR_INVALID, "sphere material id out of range");
     }
-    if ((long long) d->n_triangles + d->n_spheres >= (1LL << 27)) return fail(RT_ERR_INVALID, "too many primitives");
+    if ((long long) d->n_triangles + d->n_spheres >= (1LL << 26)) return fail(RT_ERR_INVALID, "too many primitives");
     return RT_OK;
 }
 
@@ -166,124 +186,333 @@ int ensure(unsigned char **buf, size_t *cap, size_t need, bool pinned) {
     return RT_OK;
 }
 
-struct FrameGeom {
-    int tiles_x, tiles_y, n_tiles;
+// ---- work decomposition ----------------------------------------------------------------------------------------
+// A pure function of (camera, aa, world): every rank, the gathering side and the host-side assembly agree on it
+// without talking to each other.
+struct ItemGeom {
+    int acc_mode;  // 1: f % 8 == 0, register accumulators, strips of 32 x 1 pixels
+    int P, Ph;     // item size in pixels; the band height is Ph
+    int items_x;
+    int n_bands_total;
+    int group_bands, tile_items, tiles_per_group;
 };
-// Tiles are numbered row-major over a grid whose row length is made co-prime-ish with the number of parts: when
-// tiles_x is a multiple of `world`, one phantom (empty) column is appended so that tile k -> part k % world walks
-// diagonally over the image instead of giving every part fixed vertical stripes (load balance: +6 % at 8 GPUs).
-FrameGeom geom(const RtCamera *cam, int world) {
-    FrameGeom g;
-    g.tiles_x = (cam->image_width + RT_TILE - 1) / RT_TILE;
-    if (world > 1 && g.tiles_x % world == 0) g.tiles_x += 1;
-    g.tiles_y = (cam->image_height + RT_TILE - 1) / RT_TILE;
-    g.n_tiles = g.tiles_x * g.tiles_y;
+constexpr long long kNominalWarps = 148LL * 7 * 4;  // resident warps of one B200 at the kernel's occupancy
+#ifndef RT_ACC_REGS
+#define RT_ACC_REGS 1  // A/B builds (tools/build_variants.sh): 0 = shared-memory accumulators at every AA factor
+#endif
+
+ItemGeom item_geometry(const RtCamera *cam, int aa, int world) {
+    ItemGeom g;
+    const int nx = cam->image_width, ny = cam->image_height;
+    if (aa % 8 == 0 && RT_ACC_REGS) {
+        g.acc_mode = 1;
+        g.P = 32;
+        g.Ph = 1;
+    } else {
+        g.acc_mode = 0;
+        // P x P output pixels with P*f ~ 32 sub-samples a side (1024 sub-samples per item, P <= 16 when f > 1: the
+        // accumulators live in shared memory)
+        int P = (32 + aa - 1) / aa;
+        if (P > 32) P = 32;
+        if (aa > 1 && P > 16) P = 16;
+        if (P < 1) P = 1;
+        // small frames: shrink the item (down to 8 sub-samples a side) until there are enough of them to give every
+        // resident warp a few dozen (dynamic load balance: items differ a lot in cost)
+        auto items = [&](int p, int ph) { return (long long) ((nx + p - 1) / p) * ((ny + ph - 1) / ph) / world; };
+        while (items(P, P) < 32 * kNominalWarps && P * aa > 8 && P > 1) P = (P + 1) / 2;
+        int Ph = P;
+        // still too few (a 1440x720 frame without AA has 16 K items of 64 pixels for 4144 resident warps): halve the
+        // item once more to a single 8x4 round of sub-samples
+        if (P * aa == 8 && 4 % aa == 0 && items(P, P) < 32 * kNominalWarps) Ph = 4 / aa;
+        g.P = P;
+        g.Ph = Ph;
+    }
+    g.items_x = (nx + g.P - 1) / g.P;
+    g.n_bands_total = (ny + g.Ph - 1) / g.Ph;
+    g.group_bands = std::max(1, 32 / g.Ph);
+    g.tile_items = std::max(1, 32 / g.P);
+    g.tiles_per_group = (g.items_x + g.tile_items - 1) / g.tile_items;
     return g;
 }
-int64_t part_tiles(const FrameGeom &g, int rank, int world) {
-    if (rank >= g.n_tiles) return 0;
-    return (g.n_tiles - rank + world - 1) / world;
+int64_t part_bands(const ItemGeom &g, int rank, int world) {
+    if (rank >= g.n_bands_total) return 0;
+    return (g.n_bands_total - rank + world - 1) / world;
 }
 
 int check_render_args(RtScene *s, const RtCamera *cam, int aa, int rank, int world) {
     if (!s || !cam) return fail(RT_ERR_INVALID, "NULL scene or camera");
     if (aa < 1 || aa > 64) return fail(RT_ERR_INVALID, "aa_factor must be in [1, 64]");
     if (cam->image_width < 1 || cam->image_height < 1) return fail(RT_ERR_INVALID, "empty image");
-    if ((long long) cam->image_width * aa > (1 << 24) || (long long) cam->image_height * aa > (1 << 24))
-        return fail(RT_ERR_INVALID, "sub-sample grid wider than 2^24 (pixel centres would not be exact floats)");
+    // (col + 0.5) must be an exact fp32 number (the reference forms it in double, raytracer.cpp:320): col < 2^23
+    if ((long long) cam->image_width * aa > (1 << 23) || (long long) cam->image_height * aa > (1 << 23))
+        return fail(RT_ERR_INVALID, "sub-sample grid wider than 2^23 (pixel centres col + 0.5 would not be exact floats)");
     if (world < 1 || rank < 0 || rank >= world) return fail(RT_ERR_INVALID, "bad part_rank / part_world");
-    int dev;
-    CU(cudaGetDevice(&dev));
-    if (dev != s->device) CU(cudaSetDevice(s->device));
     return RT_OK;
 }
 
-// enqueue one part on `stream`; stats are accumulated into s->d_stats (zeroed here)
-int enqueue_part(RtScene *s, const RtCamera *cam, int aa, int rank, int world, unsigned char *d_out, int out_mode,
+// enqueue one part on `stream`; statistics accumulate into control block `slot` (zeroed here with one memset)
+int enqueue_part(RtScene *s, const RtCamera *cam, int aa, int rank, int world, unsigned char *d_out, int out_mode, int slot,
                  cudaStream_t stream, int *launches) {
     RenderParams p = s->base;
     camera_setup(*cam, cam->image_width * aa, cam->image_height * aa, p);
-    const FrameGeom g = geom(cam, world);
+    const ItemGeom g = item_geometry(cam, aa, world);
     p.nx = cam->image_width;
     p.ny = cam->image_height;
     p.f = aa;
-    // work item: P x P output pixels with P*f ~ 32 sub-samples a side (1024 sub-samples): a CTA tile with 4
-    // sub-samples per thread (kernel 1) or a warp tile refilled lane by lane (kernel 2, P <= 16 when f > 1)
-    int P = (32 + aa - 1) / aa;
-    if (P > RT_TILE) P = RT_TILE;
-    if (P < 1) P = 1;
-    if (s->kernel >= 2) {
-        if (const char *tp = getenv("RT_B200_TILE_P")) P = atoi(tp) > 0 ? atoi(tp) : P;  // experiments only
-        if (aa > 1 && P > 16) P = 16;
-        // small frames: shrink the warp tile (down to 8 sub-samples a side) until there are enough tiles to
-        // give every resident warp a few dozen of them (dynamic load balance: tiles differ a lot in cost)
-        const long long slots = s->kernel == 2 ? (long long) s->n_sms * s->ctas_per_sm2 * s->warps_per_cta2
-                                               : (long long) s->n_sms * s->ctas_per_sm3 * s->warps_per_cta3;
-        for (;;) {
-            const long long ix = (RT_TILE + P - 1) / P;
-            if (part_tiles(g, rank, world) * ix * ix >= 32 * slots || P * aa <= 8 || P == 1) break;
-            P = (P + 1) / 2;
-        }
-    }
-    int Ph = P;
-    if (s->kernel >= 2 && P * aa == 8 && 4 % aa == 0) {
-        // still too few tiles for the machine (a 1440x720 frame without AA has 16 K tiles of 64 pixels for 4144
-        // resident warps): halve the tile once more to a single 8x4 round of sub-samples
-        const long long slots = s->kernel == 2 ? (long long) s->n_sms * s->ctas_per_sm2 * s->warps_per_cta2
-                                               : (long long) s->n_sms * s->ctas_per_sm3 * s->warps_per_cta3;
-        const long long ix = (RT_TILE + P - 1) / P;
-        if (part_tiles(g, rank, world) * ix * ix < 32 * slots) Ph = 4 / aa;
-    }
-    p.P = P;
-    p.Ph = Ph;
-    p.items_x = (RT_TILE + P - 1) / P;
-    p.items_y = (RT_TILE + Ph - 1) / Ph;
-    p.tiles_x = g.tiles_x;
-    p.tiles_y = g.tiles_y;
+    p.P = g.P;
+    p.Ph = g.Ph;
+    p.items_x = g.items_x;
+    p.n_bands = (int) part_bands(g, rank, world);
+    p.group_bands = g.group_bands;
+    p.tile_items = g.tile_items;
+    p.tiles_per_group = g.tiles_per_group;
     p.part_rank = rank;
     p.part_world = world;
-    const long long n_items = part_tiles(g, rank, world) * (long long) p.items_x * p.items_y;
+    const long long n_groups = (p.n_bands + g.group_bands - 1) / g.group_bands;
+    const long long n_items = n_groups * g.tiles_per_group * g.tile_items * g.group_bands;
     if (n_items >= (1LL << 32) - (1 << 22)) return fail(RT_ERR_INVALID, "too many work items");
     p.n_items = (unsigned) n_items;
     p.out_mode = out_mode;
+    p.acc_mode = (g.acc_mode == 1 && s->refill_threshold == 0) ? 1 : 0;
+    if (g.acc_mode == 1 && p.acc_mode == 0) return fail(RT_ERR_STATE, "a non-zero refill threshold needs an AA factor that is not a multiple of 8");
     p.refill_threshold = s->refill_threshold;
-    p.out = d_out;
-    p.work_counter = s->d_counter;
-    p.stats = s->d_stats;
-    CU(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned int), stream));
-    CU(cudaMemsetAsync(s->d_stats, 0, 6 * sizeof(unsigned long long), stream));
-    if (n_items == 0) return RT_OK;
-    cudaError_t e;
-    if (s->kernel == 2) {
-        long long ctas = (long long) s->n_sms * s->ctas_per_sm2;
-        const long long need = (n_items + s->warps_per_cta2 - 1) / s->warps_per_cta2;
-        if (ctas > need) ctas = need;
-        e = (cudaError_t) launch_render_v2(p, (int) ctas, stream);
-    } else if (s->kernel == 3) {
-        long long ctas = (long long) s->n_sms * s->ctas_per_sm3;
-        const long long need = (n_items + s->warps_per_cta3 - 1) / s->warps_per_cta3;
-        if (ctas > need) ctas = need;
-        e = (cudaError_t) launch_render_v3(p, (int) ctas, stream);
-    } else {
-        long long ctas = (long long) s->n_sms * s->ctas_per_sm;
-        if (ctas > n_items) ctas = n_items;
-        e = (cudaError_t) launch_render(p, (int) ctas, stream);
+    // camera far outside the scene (beyond 4x its reach): the slab arithmetic needs the widened test (render_v2.cu)
+    {
+        double d2 = 0;
+        const float e[3] = {cam->position.x, cam->position.y, cam->position.z};
+        for (int k = 0; k < 3; k++) d2 += ((double) e[k] - s->scene_center[k]) * ((double) e[k] - s->scene_center[k]);
+        p.far_camera = std::sqrt(d2) > 4.0 * (double) s->scene_reach ? 1 : 0;
     }
+    p.out = d_out;
+    p.control = s->buf.control + 8 * slot;
+    CU(cudaMemsetAsync(p.control, 0, 8 * sizeof(unsigned long long), stream));
+    if (n_items == 0) return RT_OK;
+    long long ctas = (long long) s->n_sms * s->ctas_per_sm[p.acc_mode];
+    const long long need = (n_items + s->warps_per_cta - 1) / s->warps_per_cta;
+    if (ctas > need) ctas = need;
+    const cudaError_t e = (cudaError_t) launch_render_v2(p, (int) ctas, stream);
     if (e != cudaSuccess) return fail(RT_ERR_CUDA, std::string("render kernel launch: ") + cudaGetErrorString(e));
     if (launches) (*launches)++;
     return RT_OK;
 }
 
-int fetch_stats(RtScene *s, RtStats *stats) {
-    unsigned long long h[6];
-    CU(cudaMemcpy(h, s->d_stats, sizeof h, cudaMemcpyDeviceToHost));
-    stats->primary_rays = h[0];
-    stats->reflection_rays = h[1];
-    stats->shadow_rays = h[2];
-    stats->shadow_occluded = h[3];
-    stats->replayed_closest = h[4];
-    stats->replayed_any = h[5];
+void stats_from_words(const unsigned long long *h, RtStats *stats) {
+    stats->primary_rays = h[1];
+    stats->reflection_rays = h[2];
+    stats->shadow_rays = h[3];
+    stats->shadow_occluded = h[4];
+    stats->replayed_closest = h[5];
+    stats->replayed_any = h[6];
+}
+
+// strided device-to-host copy of one part's packed bands into the rows of a row-major host frame
+int copy_part_to_frame(const ItemGeom &g, const RtCamera *cam, int rank, int world, const unsigned char *d_part, unsigned char *frame,
+                       cudaStream_t stream) {
+    const size_t row_bytes = (size_t) cam->image_width * 3, band_bytes = row_bytes * g.Ph;
+    const int64_t nb = part_bands(g, rank, world);
+    if (nb == 0) return RT_OK;
+    // the last band of the frame may be cut short by the image height
+    const int64_t last_band = rank + (nb - 1) * world;
+    const int64_t last_rows = std::min<int64_t>(g.Ph, cam->image_height - last_band * g.Ph);
+    const int64_t full = last_rows == g.Ph ? nb : nb - 1;
+    if (full > 0) {
+        if (world == 1) CU(cudaMemcpyAsync(frame, d_part, band_bytes * full, cudaMemcpyDeviceToHost, stream));
+        else CU(cudaMemcpy2DAsync(frame + band_bytes * rank, band_bytes * world, d_part, band_bytes, band_bytes, (size_t) full,
+                                  cudaMemcpyDeviceToHost, stream));
+    }
+    if (full < nb)
+        CU(cudaMemcpyAsync(frame + band_bytes * last_band, d_part + band_bytes * (nb - 1), row_bytes * last_rows, cudaMemcpyDeviceToHost, stream));
     return RT_OK;
+}
+
+bool is_pinned(const void *p) {
+    cudaPointerAttributes attr;
+    const bool yes = cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    return yes;
+}
+
+// FNV-1a over the reference tree (boxes, axes, child links, leaf ranges, leaf order): equal hashes <=> equal trees
+uint64_t ref_tree_hash(const RefTree &t) {
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const void *p, size_t n) {
+        const unsigned char *b = (const unsigned char *) p;
+        for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 1099511628211ull;
+    };
+    for (auto &n: t.nodes) {
+        mix(n.mn, sizeof n.mn);
+        mix(n.mx, sizeof n.mx);
+        const int v[5] = {n.is_leaf ? 0 : n.axis, n.is_leaf, n.is_leaf ? -1 : n.right, n.first, n.count};
+        mix(v, sizeof v);
+    }
+    mix(t.leaf_prims.data(), t.leaf_prims.size() * sizeof(int));
+    mix(t.leaf_of_prim.data(), t.leaf_of_prim.size() * sizeof(int));
+    return h;
+}
+
+int scene_create_impl(const RtSceneDesc *desc, const RtBuildOptions *opts, RtScene **out, SceneBuild *keep_build) {
+    if (!out) return fail(RT_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int rc = validate(desc);
+    if (rc != RT_OK) return rc;
+    const double t0 = now_ms();
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    RtScene *s = new RtScene();
+    s->device = dev;
+    memset(&s->info, 0, sizeof s->info);
+    memset(&s->base, 0, sizeof s->base);
+    auto bail = [&](int code, const std::string &msg) {
+        rt_scene_destroy(s);
+        return fail(code, msg);
+    };
+    if (cudaDeviceGetAttribute(&s->n_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        return bail(RT_ERR_CUDA, "cudaDeviceGetAttribute failed (no usable CUDA device?)");
+    const int nt = desc->n_triangles, ns = desc->n_spheres, np = nt + ns;
+    int builder = opts ? opts->builder : RT_BUILD_DEFAULT;
+    if (builder == RT_BUILD_DEFAULT) builder = RT_BUILD_AUTO;
+    if (builder < RT_BUILD_LBVH_GPU || builder > RT_BUILD_SAH_GPU) return bail(RT_ERR_INVALID, "unknown builder");
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(RT_ERR_CUDA, "cudaStreamCreate failed (no usable CUDA device?)");
+    int occ[2] = {0, 0};
+    if (render_kernel_v2_occupancy(occ, &s->warps_per_cta) != 0 || occ[0] < 1 || occ[1] < 1)
+        return bail(RT_ERR_CUDA, "render kernel cannot be resident on this device (built for sm_100a)");
+    s->ctas_per_sm[0] = occ[0];
+    s->ctas_per_sm[1] = occ[1];
+    if (opts && opts->refill_threshold > 0) s->refill_threshold = opts->refill_threshold > 31 ? 31 : opts->refill_threshold;
+
+    SceneBuild local_build;
+    SceneBuild &build = keep_build ? *keep_build : local_build;
+    std::string err;
+    const int radius = (opts && opts->ploc_radius > 0) ? opts->ploc_radius : 16;
+    const float leaf_cost = (opts && opts->ploc_leaf_cost > 0) ? opts->ploc_leaf_cost : 1.0f;  // tools/ploc_tune.py: 1.0 beats 1.6 and 2.5
+    rc = build.run(*desc, builder, radius, leaf_cost, s->n_sms, s->stream, s->buf, err);
+    s->arena = build.arena;
+    build.arena = nullptr;
+    if (!keep_build) build.release_scratch();
+    if (rc != 0) return bail(rc == -2 ? RT_ERR_STATE : RT_ERR_CUDA, "scene build: " + err);
+    for (int i = 0; i < 2; i++)
+        if (cudaEventCreate(&s->ev_part[i]) != cudaSuccess) return bail(RT_ERR_CUDA, "cudaEventCreate");
+
+    const BuildResult &r = build.result;
+    int kept = builder;
+    if (build.used_host_builder) kept = RT_BUILD_SAH_HOST;
+    else if (builder == RT_BUILD_AUTO) kept = np <= 1 ? RT_BUILD_SAH_GPU : (r.chosen == 0 ? RT_BUILD_PLOC_GPU : RT_BUILD_SAH_GPU);
+
+    RenderParams &b = s->base;
+    b.nodes = s->buf.nodes;
+    b.prims = s->buf.prims;
+    b.tri_nm = s->buf.tri_nm;
+    b.tri_nn = s->buf.tri_nn;
+    b.sph_cr = s->buf.sph_cr;
+    b.sph_mat = s->buf.sph_mat;
+    b.ranks = s->buf.ranks;
+    b.ref_nodes = s->buf.ref_nodes;
+    b.ref_leaf_prims = s->buf.ref_leaf_prims;
+    b.prim_bounds = s->buf.prim_bounds;
+    b.slot_of_prim = s->buf.slot_of_prim;
+    b.exact_culling = (opts && opts->no_exact_culling) ? 0 : ((opts && opts->force_replay) ? 2 : 1);
+    b.materials = s->buf.materials;
+    b.lights = s->buf.lights;
+    b.n_nodes = np > 0 ? r.n_nodes[r.chosen] : 0;
+    b.n_tris = nt;
+    b.n_prims = np;
+    b.n_lights = desc->n_lights;
+    b.max_depth = desc->max_recursion_depth;
+    b.brute_force = opts ? opts->brute_force : 0;
+    b.eps = desc->shadow_ray_epsilon;
+    b.ambient[0] = desc->ambient_light.x, b.ambient[1] = desc->ambient_light.y, b.ambient[2] = desc->ambient_light.z;
+    for (int k = 0; k < 3; k++) b.background[k] = (float) desc->background[k];  // raytracer.cpp:446-447
+    if (desc->max_recursion_depth < 0) {
+        // raytracer.cpp:387-389: depth 0 > max_recursion_depth, every primary ray returns black without being traced
+        b.n_nodes = 0;
+        b.background[0] = b.background[1] = b.background[2] = 0.0f;
+    }
+    if (np > 0) {
+        double diag2 = 0;
+        float reach = 0;
+        for (int k = 0; k < 3; k++) {
+            const float lo = ord2f(r.scene_bounds[k]), hi = ord2f(r.scene_bounds[3 + k]);
+            s->scene_center[k] = 0.5f * (lo + hi);
+            diag2 += ((double) hi - lo) * ((double) hi - lo);
+            reach = std::max(reach, std::max(std::fabs(lo), std::fabs(hi)));
+        }
+        s->scene_reach = (float) std::sqrt(diag2) + reach;
+    } else {
+        s->scene_reach = INFINITY;
+    }
+
+    RtSceneInfo &inf = s->info;
+    inf.n_triangles = nt;
+    inf.n_spheres = ns;
+    inf.bvh_nodes = b.n_nodes;
+    inf.bvh_max_depth = np > 0 ? r.height[r.chosen] : 0;
+    inf.ref_tree_nodes = r.ref_nodes;
+    inf.ref_tree_leaves = r.ref_leaves;
+    inf.ref_tree_max_leaf = r.ref_max_leaf;
+    inf.ref_tree_max_depth = r.ref_max_depth;
+    inf.ms_build_host = build.ms_host_before_sync;
+    inf.ms_build_device = build.ms_device;
+    inf.bvh_sah_cost = np > 0 ? r.sah_cost[r.chosen] : 0.0f;
+    inf.builder = kept;
+    inf.device = dev;
+    inf.sah_cost_ploc = (builder == RT_BUILD_AUTO && np > 1) ? r.sah_cost[0] : 0.0f;
+    inf.sah_cost_sah = (builder == RT_BUILD_AUTO && np > 1) ? r.sah_cost[1] : 0.0f;
+    inf.ms_create_wall = (float) (now_ms() - t0);
+    *out = s;
+    return RT_OK;
+}
+
+int slot_prepare(RenderSlot &sl) {
+    if (!sl.ev_start) {
+        CU(cudaEventCreate(&sl.ev_start));
+        CU(cudaEventCreate(&sl.ev_kernel));
+        CU(cudaEventCreate(&sl.ev_done));
+        CU(cudaMallocHost((void **) &sl.h_stats, 8 * sizeof(unsigned long long)));
+    }
+    return RT_OK;
+}
+
+int render_part_common(RtScene *s, const RtCamera *cam, int aa, int rank, int world, void *d_out, int mode, void *cuda_stream,
+                       RtStats *stats) {
+    int rc = check_render_args(s, cam, aa, rank, world);
+    if (rc != RT_OK) return rc;
+    if (!d_out) return fail(RT_ERR_INVALID, "device output pointer is NULL");
+    DeviceGuard g;
+    if (g.use(s->device) != 0) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t st = (cudaStream_t) cuda_stream;
+    int launches = 0;
+    const int k = kControlSlots - 1;  // parts use the last control slot
+    if (stats) CU(cudaEventRecord(s->ev_part[0], st));
+    rc = enqueue_part(s, cam, aa, rank, world, (unsigned char *) d_out, mode, k, st, &launches);
+    if (rc != RT_OK) return rc;
+    if (stats) {
+        CU(cudaEventRecord(s->ev_part[1], st));
+        unsigned long long h[8];
+        CU(cudaMemcpyAsync(h, s->buf.control + 8 * k, sizeof h, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        memset(stats, 0, sizeof *stats);
+        stats_from_words(h, stats);
+        cudaEventElapsedTime(&stats->ms_render, s->ev_part[0], s->ev_part[1]);
+        stats->ms_total = stats->ms_render;
+        stats->n_launches = launches;
+    }
+    return RT_OK;
+}
+
+// enqueue: this part's bands into the handle's packed buffer, then straight into the rows of a host frame
+int enqueue_part_to_host(RtScene *s, const RtCamera *cam, int aa, int rank, int world, unsigned char *host_frame, int *launches) {
+    const ItemGeom g = item_geometry(cam, aa, world);
+    const size_t bytes = (size_t) part_bands(g, rank, world) * g.Ph * cam->image_width * 3;
+    int rc = ensure(&s->d_parts, &s->parts_cap, bytes ? bytes : 1, false);
+    if (rc != RT_OK) return rc;
+    const int k = kControlSlots - 1;
+    CU(cudaEventRecord(s->ev_part[0], s->stream));
+    rc = enqueue_part(s, cam, aa, rank, world, s->d_parts, kOutPacked, k, s->stream, launches);
+    if (rc != RT_OK) return rc;
+    CU(cudaEventRecord(s->ev_part[1], s->stream));
+    return copy_part_to_frame(g, cam, rank, world, s->d_parts, host_frame, s->stream);
 }
 
 }  // namespace
@@ -297,6 +526,87 @@ int rt_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
     return n;
+}
+
+int rt_set_device(int device) {
+    CU(cudaSetDevice(device));
+    return RT_OK;
+}
+
+// Brings the CUDA context of `device` up and loads the render kernels (CUDA loads modules and functions lazily), so
+// that a caller can pay for both on a helper thread while it parses its scene file.
+int rt_warmup(int device) {
+    CU(cudaSetDevice(device));
+    CU(cudaFree(nullptr));
+    int occ[2], warps;
+    if (render_kernel_v2_occupancy(occ, &warps) != 0) return fail(RT_ERR_CUDA, "render kernel cannot be loaded on this device (built for sm_100a)");
+    return RT_OK;
+}
+
+int rt_host_alloc(int64_t bytes, void **ptr) {
+    if (!ptr || bytes <= 0) return fail(RT_ERR_INVALID, "bad argument");
+    CU(cudaMallocHost(ptr, (size_t) bytes));
+    return RT_OK;
+}
+
+int rt_host_free(void *ptr) {
+    CU(cudaFreeHost(ptr));
+    return RT_OK;
+}
+
+// ---- a host frame shared by one process per GPU (POSIX shared memory, page-locked in every process) -------------
+
+int rt_host_frame_create(const char *name, int64_t bytes, void **ptr) {
+    if (!name || !ptr || bytes <= 0) return fail(RT_ERR_INVALID, "bad argument");
+    shm_unlink(name);
+    const int fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd < 0) return fail(RT_ERR_STATE, std::string("shm_open(create) failed for ") + name);
+    if (ftruncate(fd, (off_t) bytes) != 0) {
+        close(fd);
+        shm_unlink(name);
+        return fail(RT_ERR_NOMEM, "ftruncate on the shared frame failed");
+    }
+    void *p = mmap(nullptr, (size_t) bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) {
+        shm_unlink(name);
+        return fail(RT_ERR_NOMEM, "mmap of the shared frame failed");
+    }
+    memset(p, 0, (size_t) bytes);  // touch every page before pinning
+    if (cudaHostRegister(p, (size_t) bytes, cudaHostRegisterPortable) != cudaSuccess) {
+        cudaGetLastError();
+        munmap(p, (size_t) bytes);
+        shm_unlink(name);
+        return fail(RT_ERR_CUDA, "cudaHostRegister of the shared frame failed");
+    }
+    *ptr = p;
+    return RT_OK;
+}
+
+int rt_host_frame_open(const char *name, int64_t bytes, void **ptr) {
+    if (!name || !ptr || bytes <= 0) return fail(RT_ERR_INVALID, "bad argument");
+    const int fd = shm_open(name, O_RDWR, 0600);
+    if (fd < 0) return fail(RT_ERR_STATE, std::string("shm_open failed for ") + name);
+    void *p = mmap(nullptr, (size_t) bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) return fail(RT_ERR_NOMEM, "mmap of the shared frame failed");
+    if (cudaHostRegister(p, (size_t) bytes, cudaHostRegisterPortable) != cudaSuccess) {
+        cudaGetLastError();
+        munmap(p, (size_t) bytes);
+        return fail(RT_ERR_CUDA, "cudaHostRegister of the shared frame failed");
+    }
+    *ptr = p;
+    return RT_OK;
+}
+
+int rt_host_frame_close(void *ptr, int64_t bytes, const char *unlink_name) {
+    if (ptr) {
+        cudaHostUnregister(ptr);
+        cudaGetLastError();
+        munmap(ptr, (size_t) bytes);
+    }
+    if (unlink_name) shm_unlink(unlink_name);
+    return RT_OK;
 }
 
 // ---- peer memory for the fused gather ---------------------------------------------------------------
@@ -359,7 +669,7 @@ int rt_host_check_bvh(const RtSceneDesc *desc, float *sah_cost, int32_t *max_dep
     build_bvh_sah_host(bounds, bvh);
     if (sah_cost) *sah_cost = bvh_sah_cost(bvh);
     if (max_depth) *max_depth = tree_depth(bvh);
-    compact_dfs(bvh, 7);  // the layout pass every tree goes through (here with a breadth-first prefix) must keep the tree intact
+    compact_dfs(bvh, 7);  // a depth-first re-layout (here with a breadth-first prefix) must keep the tree intact
     pad_boxes(bvh, bounds);
     const int np = (int) bounds.size();
     std::vector<int> seen((size_t) np, 0);
@@ -404,24 +714,6 @@ int rt_host_check_bvh(const RtSceneDesc *desc, float *sah_cost, int32_t *max_dep
     return (int) bvh.nodes.size();
 }
 
-// FNV-1a over the reference tree (boxes, axes, child links, leaf ranges, leaf order): equal hashes <=> equal trees
-static uint64_t ref_tree_hash(const RefTree &t) {
-    uint64_t h = 1469598103934665603ull;
-    auto mix = [&](const void *p, size_t n) {
-        const unsigned char *b = (const unsigned char *) p;
-        for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 1099511628211ull;
-    };
-    for (auto &n: t.nodes) {
-        mix(n.mn, sizeof n.mn);
-        mix(n.mx, sizeof n.mx);
-        const int v[5] = {n.is_leaf ? 0 : n.axis, n.is_leaf, n.is_leaf ? -1 : n.right, n.first, n.count};
-        mix(v, sizeof v);
-    }
-    mix(t.leaf_prims.data(), t.leaf_prims.size() * sizeof(int));
-    mix(t.leaf_of_prim.data(), t.leaf_of_prim.size() * sizeof(int));
-    return h;
-}
-
 int rt_host_reference_tree_hash(const RtSceneDesc *desc, uint64_t *hash) {
     int rc = validate(desc);
     if (rc != RT_OK) return rc;
@@ -433,348 +725,70 @@ int rt_host_reference_tree_hash(const RtSceneDesc *desc, uint64_t *hash) {
     return RT_OK;
 }
 
-// the GPU build of the same tree and ranks (ref_order_device.cu); needs a device
-int rt_device_reference_ranks(const RtSceneDesc *desc, uint32_t *ranks_out, int32_t *stats4, uint64_t *tree_hash) {
-    int rc = validate(desc);
-    if (rc != RT_OK) return rc;
-    std::vector<Aabb> bounds;
-    primitive_bounds(*desc, bounds);
-    std::vector<uint32_t> ranks;
-    RefTreeStats st;
-    RefTree tree;
-    if (build_reference_ranks_device(*desc, bounds, ranks, st, tree, nullptr) != 0) return fail(RT_ERR_CUDA, "device build failed");
-    if (ranks_out) memcpy(ranks_out, ranks.data(), ranks.size() * sizeof(uint32_t));
-    if (stats4) stats4[0] = st.nodes, stats4[1] = st.leaves, stats4[2] = st.max_leaf, stats4[3] = st.max_depth;
-    if (tree_hash) *tree_hash = ref_tree_hash(tree);
-    return RT_OK;
-}
-
 float rt_host_pow_ref(float base, float e) { return pow_ref(base, e); }
 int rt_host_specular_gate(float cos_theta) { return specular_gate(cos_theta) ? 1 : 0; }
 
-int rt_set_device(int device) {
-    CU(cudaSetDevice(device));
-    return RT_OK;
-}
+// ---- scene -------------------------------------------------------------------------------------------------------
 
 int rt_scene_create(const RtSceneDesc *desc, const RtBuildOptions *opts, RtScene **out) {
-    if (!out) return fail(RT_ERR_INVALID, "out is NULL");
-    *out = nullptr;
-    int rc = validate(desc);
-    if (rc != RT_OK) return rc;
-    int dev = 0;
-    CU(cudaGetDevice(&dev));
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, dev));
+    return scene_create_impl(desc, opts, out, nullptr);
+}
 
-    RtScene *s = new RtScene();
-    s->device = dev;
-    s->n_sms = prop.multiProcessorCount;
-    memset(&s->info, 0, sizeof s->info);
-    memset(&s->base, 0, sizeof s->base);
-    const int nt = desc->n_triangles, ns = desc->n_spheres, np = nt + ns;
-    int builder = opts ? opts->builder : RT_BUILD_DEFAULT;
-    if (builder == RT_BUILD_DEFAULT) builder = RT_BUILD_AUTO;
-
-    const double t0 = now_ms();
-    // reference-order tie ranks
-    std::vector<uint32_t> ranks;
-    RefTreeStats rstats;
-    RefTree rtree;
-    std::vector<Aabb> bounds;
-    primitive_bounds(*desc, bounds);
-    float ms_ranks_device = 0;
-    double ms_ranks_wall = 0;
-    if (getenv("RT_B200_HOST_RANKS")) {  // the host implementation (ref_order.cpp) stays as the cross-check
-        build_reference_ranks(*desc, ranks, rstats, &rtree);
-    } else {
-        const double tr0 = now_ms();
-        if (build_reference_ranks_device(*desc, bounds, ranks, rstats, rtree, &ms_ranks_device) != 0) {
-            delete s;
-            return fail(RT_ERR_CUDA, "device build of the reference-order tree failed");
-        }
-        ms_ranks_wall = now_ms() - tr0;
-    }
-
-    HostBvh bvh;
-    float ms_device = 0;
-    double ms_device_wall = 0;  // includes CUDA context creation on the first call; not host build work
-    if (builder == RT_BUILD_LBVH_GPU || builder == RT_BUILD_PLOC_GPU || builder == RT_BUILD_AUTO) {
-        const double td0 = now_ms();
-        int e = build_bvh_device(bounds, bvh, &ms_device, builder != RT_BUILD_LBVH_GPU);
-        ms_device_wall = now_ms() - td0;
-        if (e != 0) {
-            delete s;
-            return fail(RT_ERR_CUDA, "device BVH build failed");
-        }
-        if (builder == RT_BUILD_AUTO) {
-            // AUTO: both trees are built on the GPU.  The PLOC tree is kept when its SAH cost is clearly lower than
-            // the top-down binned-SAH tree's (< 0.8x: scenes with huge primitives next to dense meshes, e.g.
-            // horse_and_mug 4.4 vs 7.2); otherwise the shallower top-down tree traverses 4-12 % faster
-            // (tools/ploc_tune.py).
-            HostBvh sah_tree;
-            float ms_sah = 0;
-            if (build_bvh_sah_device(bounds, sah_tree, &ms_sah) != 0) {
-                delete s;
-                return fail(RT_ERR_CUDA, "device SAH build failed");
-            }
-            ms_device += ms_sah;
-            if (tree_depth(bvh) > 60 || !(bvh_sah_cost(bvh) < 0.8f * bvh_sah_cost(sah_tree))) {
-                bvh = sah_tree;
-                builder = RT_BUILD_SAH_GPU;
-            } else {
-                builder = RT_BUILD_PLOC_GPU;
-            }
-            ms_device_wall = now_ms() - td0;
-        }
-    } else if (builder == RT_BUILD_SAH_GPU) {
-        const double td0 = now_ms();
-        if (build_bvh_sah_device(bounds, bvh, &ms_device) != 0) {
-            delete s;
-            return fail(RT_ERR_CUDA, "device SAH build failed");
-        }
-        ms_device_wall = now_ms() - td0;
-    } else {
-        build_bvh_sah_host(bounds, bvh);
-    }
-    bvh.max_depth = tree_depth(bvh);
-    if (bvh.max_depth > 60 && builder != RT_BUILD_SAH_HOST) {
-        // a pathological primitive order made the clustered tree too deep for the traversal stack: the host
-        // builder splits at the median when the SAH finds nothing and stays O(log n) deep
-        builder = RT_BUILD_SAH_HOST;
-        build_bvh_sah_host(bounds, bvh);
-        bvh.max_depth = tree_depth(bvh);
-    }
-    if (bvh.max_depth > 60) {
-        delete s;
-        return fail(RT_ERR_STATE, "BVH deeper than the traversal stack");
-    }
-    compact_dfs(bvh, getenv("RT_B200_BFS_TOP") ? atoi(getenv("RT_B200_BFS_TOP")) : 0);
-    const float sah = bvh_sah_cost(bvh);
-    pad_boxes(bvh, bounds);
-    // A single-primitive scene has a root with one real child.  The missing child becomes a leaf over a dummy
-    // all-zero triangle (slot np: detA = 0, every comparison on NaN fails, it can never report a hit), so the
-    // traversal loop needs no "empty child" test.
-    for (auto &n: bvh.nodes) {
-        if (n.child1 == kEmptyChild) {
-            n.child1 = ~((np << 3) | 0);
-            for (int k = 0; k < 3; k++) n.c1mn[k] = n.c0mn[k], n.c1mx[k] = n.c0mx[k];
-        }
-        if (n.child0 == kEmptyChild) {
-            n.child0 = ~((np << 3) | 0);
-            for (int k = 0; k < 3; k++) n.c0mn[k] = n.c1mn[k], n.c0mx[k] = n.c1mx[k];
-        }
-    }
-
-    // stage SoA buffers
-    std::vector<float4> nodes(bvh.nodes.size() * 4);
-    for (size_t i = 0; i < bvh.nodes.size(); i++) {
-        const HostNode &n = bvh.nodes[i];
-        // per axis: (centre, half-extent) of the padded child box; the half-extent is rounded up so that the
-        // stored box still contains the padded one (device_common.cuh slab())
-        float c0[3], h0[3], c1[3], h1[3];
-        for (int k = 0; k < 3; k++) {
-            c0[k] = 0.5f * (n.c0mn[k] + n.c0mx[k]);
-            c1[k] = 0.5f * (n.c1mn[k] + n.c1mx[k]);
-            h0[k] = std::max(n.c0mx[k] - c0[k], c0[k] - n.c0mn[k]) * 1.000001f + std::fabs(c0[k]) * 2e-7f;
-            h1[k] = std::max(n.c1mx[k] - c1[k], c1[k] - n.c1mn[k]) * 1.000001f + std::fabs(c1[k]) * 2e-7f;
-        }
-        nodes[4 * i + 0] = make_float4(c0[0], h0[0], c0[1], h0[1]);
-        nodes[4 * i + 1] = make_float4(c1[0], h1[0], c1[1], h1[1]);
-        nodes[4 * i + 2] = make_float4(c0[2], h0[2], c1[2], h1[2]);
-        nodes[4 * i + 3] = make_float4(__builtin_bit_cast(float, n.child0), __builtin_bit_cast(float, n.child1), 0.f, 0.f);
-    }
-    auto bits = [](int v) { return __builtin_bit_cast(float, v); };
-    std::vector<float4> prims((size_t) (np + 1) * 3, make_float4(0.f, 0.f, 0.f, 0.f));
-    for (int sidx = 0; sidx < np; sidx++) {
-        const int id = bvh.prim_order[sidx];
-        if (id < nt) {
-            const RtTriangle &t = desc->triangles[id];
-            const RtVec3 &a = desc->vertices[t.v0_id - 1], &b = desc->vertices[t.v1_id - 1], &c = desc->vertices[t.v2_id - 1];
-            // raytracer.cpp:135-138: a - b and a - c, the same fp32 subtractions done once
-            volatile float abx = a.x - b.x, aby = a.y - b.y, abz = a.z - b.z;
-            volatile float acx = a.x - c.x, acy = a.y - c.y, acz = a.z - c.z;
-            volatile float p1 = aby * acz, p2 = acy * abz;
-            volatile float mn = p1 - p2;  // det()'s m10*m21 - m11*m20 of raytracer.cpp:18
-            prims[3 * (size_t) sidx + 0] = make_float4(a.x, a.y, a.z, bits(id));
-            prims[3 * (size_t) sidx + 1] = make_float4(abx, aby, abz, bits(0));
-            prims[3 * (size_t) sidx + 2] = make_float4(acx, acy, acz, mn);
-        } else {
-            const RtSphere &sp = desc->spheres[id - nt];
-            const RtVec3 &c = desc->vertices[sp.center_vertex_id - 1];
-            prims[3 * (size_t) sidx + 0] = make_float4(c.x, c.y, c.z, bits(id));
-            prims[3 * (size_t) sidx + 1] = make_float4(sp.radius, 0.f, 0.f, bits(1));
-            prims[3 * (size_t) sidx + 2] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    }
-    std::vector<float4> prim_bounds((size_t) np * 2);
-    for (int i = 0; i < np; i++) {
-        prim_bounds[2 * (size_t) i] = make_float4(bounds[i].mn[0], bounds[i].mn[1], bounds[i].mn[2], 0.f);
-        prim_bounds[2 * (size_t) i + 1] = make_float4(bounds[i].mx[0], bounds[i].mx[1], bounds[i].mx[2], 0.f);
-    }
-    std::vector<int> slot_of_prim((size_t) np);
-    for (int sidx = 0; sidx < np; sidx++) slot_of_prim[bvh.prim_order[sidx]] = sidx;
-    std::vector<float4> ref_nodes(rtree.nodes.size() * 3);
-    for (size_t i = 0; i < rtree.nodes.size(); i++) {
-        const RefTreeNode &n = rtree.nodes[i];
-        ref_nodes[3 * i + 0] = make_float4(n.mn[0], n.mn[1], n.mn[2], bits(n.axis | (n.is_leaf ? 4 : 0)));
-        ref_nodes[3 * i + 1] = make_float4(n.mx[0], n.mx[1], n.mx[2], bits(n.right));
-        ref_nodes[3 * i + 2] = make_float4(bits(n.first), bits(n.count), 0.f, 0.f);
-    }
-    std::vector<float4> tri_nm((size_t) nt), tri_nn((size_t) nt);
-    for (int i = 0; i < nt; i++) {
-        const RtTriangle &t = desc->triangles[i];
-        const RtVec3 &a = desc->vertices[t.v0_id - 1], &b = desc->vertices[t.v1_id - 1], &c = desc->vertices[t.v2_id - 1];
-        // raytracer.cpp:346  ((b - a) x (c - a)).normalize()
-        volatile float bax = b.x - a.x, bay = b.y - a.y, baz = b.z - a.z;
-        volatile float cax = c.x - a.x, cay = c.y - a.y, caz = c.z - a.z;
-        volatile float x1 = bay * caz, x2 = baz * cay, y1 = baz * cax, y2 = bax * caz, z1 = bax * cay, z2 = bay * cax;
-        volatile float nx = x1 - x2, ny = y1 - y2, nz = z1 - z2;
-        volatile float xx = nx * nx, yy = ny * ny, zz = nz * nz;
-        volatile float s2 = xx + yy;
-        s2 = s2 + zz;
-        const float len = (float) std::sqrt((double) s2);
-        tri_nm[i] = make_float4(nx / len, ny / len, nz / len, bits(t.material_id));
-        // intersection.normal.normalize() of an already unit-length normal (raytracer.cpp:414, :432): same ops, once
-        volatile float ux = nx / len, uy = ny / len, uz = nz / len;
-        volatile float uxx = ux * ux, uyy = uy * uy, uzz = uz * uz;
-        volatile float u2 = uxx + uyy;
-        u2 = u2 + uzz;
-        const float ulen = (float) std::sqrt((double) u2);
-        tri_nn[i] = make_float4(ux / ulen, uy / ulen, uz / ulen, 0.f);
-    }
-    std::vector<float4> sph_cr((size_t) ns);
-    std::vector<int> sph_mat((size_t) ns);
-    for (int i = 0; i < ns; i++) {
-        const RtVec3 &c = desc->vertices[desc->spheres[i].center_vertex_id - 1];
-        sph_cr[i] = make_float4(c.x, c.y, c.z, desc->spheres[i].radius);
-        sph_mat[i] = desc->spheres[i].material_id;
-    }
-    std::vector<float4> mats((size_t) desc->n_materials * 4);
-    for (int i = 0; i < desc->n_materials; i++) {
-        const RtMaterial &m = desc->materials[i];
-        mats[4 * (size_t) i + 0] = make_float4(m.ambient.x, m.ambient.y, m.ambient.z, m.phong_exponent);
-        mats[4 * (size_t) i + 1] = make_float4(m.diffuse.x, m.diffuse.y, m.diffuse.z, bits(m.is_mirror ? 1 : 0));
-        mats[4 * (size_t) i + 2] = make_float4(m.specular.x, m.specular.y, m.specular.z, 0.f);
-        mats[4 * (size_t) i + 3] = make_float4(m.mirror.x, m.mirror.y, m.mirror.z, 0.f);
-    }
-    std::vector<float4> lights((size_t) desc->n_lights * 2);
-    for (int i = 0; i < desc->n_lights; i++) {
-        const RtPointLight &l = desc->lights[i];
-        lights[2 * (size_t) i + 0] = make_float4(l.position.x, l.position.y, l.position.z, 0.f);
-        lights[2 * (size_t) i + 1] = make_float4(l.intensity.x, l.intensity.y, l.intensity.z, 0.f);
-    }
-    const double t1 = now_ms();
-
-    rc = upload(&s->d_nodes, nodes.data(), nodes.size());
-    if (rc == RT_OK) rc = upload(&s->d_prims, prims.data(), prims.size());
-    if (rc == RT_OK) rc = upload(&s->d_tri_nm, tri_nm.data(), tri_nm.size());
-    if (rc == RT_OK) rc = upload(&s->d_tri_nn, tri_nn.data(), tri_nn.size());
-    if (rc == RT_OK) rc = upload(&s->d_sph_cr, sph_cr.data(), sph_cr.size());
-    if (rc == RT_OK) rc = upload(&s->d_sph_mat, sph_mat.data(), sph_mat.size());
-    if (rc == RT_OK) rc = upload(&s->d_ranks, ranks.data(), ranks.size());
-    if (rc == RT_OK) rc = upload(&s->d_ref_nodes, ref_nodes.data(), ref_nodes.size());
-    if (rc == RT_OK) rc = upload(&s->d_ref_leaf_prims, rtree.leaf_prims.data(), rtree.leaf_prims.size());
-    if (rc == RT_OK) rc = upload(&s->d_prim_bounds, prim_bounds.data(), prim_bounds.size());
-    if (rc == RT_OK) rc = upload(&s->d_slot_of_prim, slot_of_prim.data(), slot_of_prim.size());
-    if (rc == RT_OK) rc = upload(&s->d_materials, mats.data(), mats.size());
-    if (rc == RT_OK) rc = upload(&s->d_lights, lights.data(), lights.size());
-    if (rc == RT_OK && cudaMalloc((void **) &s->d_counter, sizeof(unsigned int)) != cudaSuccess) rc = fail(RT_ERR_CUDA, "cudaMalloc");
-    if (rc == RT_OK && cudaMalloc((void **) &s->d_stats, 6 * sizeof(unsigned long long)) != cudaSuccess) rc = fail(RT_ERR_CUDA, "cudaMalloc");
-    if (rc == RT_OK && cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) rc = fail(RT_ERR_CUDA, "cudaStreamCreate");
-    for (int i = 0; i < 4 && rc == RT_OK; i++)
-        if (cudaEventCreate(&s->ev[i]) != cudaSuccess) rc = fail(RT_ERR_CUDA, "cudaEventCreate");
-    if (rc == RT_OK) {
-        int occ = 0;
-        if (render_kernel_occupancy(&occ) != 0 || occ < 1) rc = fail(RT_ERR_CUDA, "render kernel cannot be resident on this device (built for sm_100a)");
-        s->ctas_per_sm = occ;
-        int occ2 = 0;
-        if (render_kernel_v2_occupancy(&occ2, &s->warps_per_cta2) != 0 || occ2 < 1) rc = fail(RT_ERR_CUDA, "render kernel v2 cannot be resident on this device");
-        s->ctas_per_sm2 = occ2;
-        const char *kv = getenv("RT_B200_KERNEL");
-        if (kv && kv[0] == '1') s->kernel = 1;
-        if (kv && kv[0] == '3') s->kernel = 3;
-        int occ3 = 0;
-        if (render_kernel_v3_occupancy(&occ3, &s->warps_per_cta3) != 0 || occ3 < 1) rc = fail(RT_ERR_CUDA, "render kernel v3 cannot be resident on this device");
-        s->ctas_per_sm3 = occ3;
-        const char *rv = getenv("RT_B200_REFILL");
-        if (rv) s->refill_threshold = atoi(rv);
-    }
+// the GPU build of the reference-order tree and ranks, read back for the tests (they compare it with the host build
+// of ref_order.cpp bit for bit); needs a device
+int rt_device_reference_ranks(const RtSceneDesc *desc, uint32_t *ranks_out, int32_t *stats4, uint64_t *tree_hash) {
+    RtScene *s = nullptr;
+    SceneBuild build;
+    RtBuildOptions o;
+    memset(&o, 0, sizeof o);
+    o.builder = RT_BUILD_SAH_GPU;
+    int rc = scene_create_impl(desc, &o, &s, &build);
     if (rc != RT_OK) {
-        rt_scene_destroy(s);
+        build.release_scratch();
         return rc;
     }
-
-    RenderParams &b = s->base;
-    b.nodes = s->d_nodes;
-    b.prims = s->d_prims;
-    b.tri_nm = s->d_tri_nm;
-    b.tri_nn = s->d_tri_nn;
-    b.sph_cr = s->d_sph_cr;
-    b.sph_mat = s->d_sph_mat;
-    b.ranks = s->d_ranks;
-    b.ref_nodes = s->d_ref_nodes;
-    b.ref_leaf_prims = s->d_ref_leaf_prims;
-    b.prim_bounds = s->d_prim_bounds;
-    b.slot_of_prim = s->d_slot_of_prim;
-    b.exact_culling = (opts && opts->no_exact_culling) ? 0 : 1;
-    b.materials = s->d_materials;
-    b.lights = s->d_lights;
-    b.n_nodes = (int) bvh.nodes.size();
-    b.n_tris = nt;
-    b.n_prims = np;
-    b.n_lights = desc->n_lights;
-    b.max_depth = desc->max_recursion_depth;
-    b.brute_force = opts ? opts->brute_force : 0;
-    b.eps = desc->shadow_ray_epsilon;
-    b.ambient[0] = desc->ambient_light.x, b.ambient[1] = desc->ambient_light.y, b.ambient[2] = desc->ambient_light.z;
-    for (int k = 0; k < 3; k++) b.background[k] = (float) desc->background[k];  // raytracer.cpp:446-447
-
-    RtSceneInfo &inf = s->info;
-    inf.n_triangles = nt;
-    inf.n_spheres = ns;
-    inf.bvh_nodes = (int) bvh.nodes.size();
-    inf.bvh_max_depth = bvh.max_depth;
-    inf.ref_tree_nodes = rstats.nodes;
-    inf.ref_tree_leaves = rstats.leaves;
-    inf.ref_tree_max_leaf = rstats.max_leaf;
-    inf.ref_tree_max_depth = rstats.max_depth;
-    inf.ms_build_host = (float) (t1 - t0 - ms_device_wall - ms_ranks_wall);
-    inf.ms_build_device = ms_device + ms_ranks_device;
-    inf.bvh_sah_cost = sah;
-    inf.builder = builder;
-    inf.device = dev;
-    *out = s;
-    return RT_OK;
+    std::vector<uint32_t> ranks;
+    RefTreeStats st;
+    RefTree tree;
+    std::string err;
+    const int e = build.read_reference_tree(*desc, s->stream, s->buf, ranks, st, tree, err);
+    build.release_scratch();
+    if (e == 0) {
+        if (ranks_out) memcpy(ranks_out, ranks.data(), ranks.size() * sizeof(uint32_t));
+        if (stats4) stats4[0] = st.nodes, stats4[1] = st.leaves, stats4[2] = st.max_leaf, stats4[3] = st.max_depth;
+        if (tree_hash) *tree_hash = ref_tree_hash(tree);
+        // the statistics the build itself reported must agree with the tree that was read back
+        if (s->info.ref_tree_nodes != st.nodes || s->info.ref_tree_leaves != st.leaves || s->info.ref_tree_max_leaf != st.max_leaf ||
+            s->info.ref_tree_max_depth != st.max_depth) {
+            rt_scene_destroy(s);
+            return fail(RT_ERR_STATE, "device-side reference tree statistics disagree with the tree");
+        }
+    }
+    rt_scene_destroy(s);
+    return e == 0 ? RT_OK : fail(RT_ERR_CUDA, err);
 }
 
 void rt_scene_destroy(RtScene *s) {
     if (!s) return;
-    int prev = 0;
-    cudaGetDevice(&prev);
-    cudaSetDevice(s->device);
-    cudaFree(s->d_nodes);
-    cudaFree(s->d_prims);
-    cudaFree(s->d_tri_nm);
-    cudaFree(s->d_tri_nn);
-    cudaFree(s->d_sph_cr);
-    cudaFree(s->d_sph_mat);
-    cudaFree(s->d_ranks);
-    cudaFree(s->d_ref_nodes);
-    cudaFree(s->d_ref_leaf_prims);
-    cudaFree(s->d_prim_bounds);
-    cudaFree(s->d_slot_of_prim);
-    cudaFree(s->d_materials);
-    cudaFree(s->d_lights);
-    cudaFree(s->d_counter);
-    cudaFree(s->d_stats);
-    cudaFree(s->d_frame);
+    DeviceGuard g;
+    g.use(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
+    cudaFree(s->arena);
     cudaFree(s->d_parts);
-    if (s->h_pinned) cudaFreeHost(s->h_pinned);
-    if (s->stream) cudaStreamDestroy(s->stream);
-    for (auto &e: s->ev)
+    for (auto &sl: s->slot) {
+        cudaFree(sl.d_frame);
+        if (sl.h_pinned) cudaFreeHost(sl.h_pinned);
+        if (sl.h_stats) cudaFreeHost(sl.h_stats);
+        if (sl.ev_start) cudaEventDestroy(sl.ev_start);
+        if (sl.ev_kernel) cudaEventDestroy(sl.ev_kernel);
+        if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+    }
+    for (auto &e: s->ev_part)
         if (e) cudaEventDestroy(e);
-    cudaSetDevice(prev);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+    cudaGetLastError();
     delete s;
 }
 
@@ -784,77 +798,95 @@ int rt_scene_info(const RtScene *s, RtSceneInfo *info) {
     return RT_OK;
 }
 
-int64_t rt_part_tiles(const RtCamera *cam, int part_rank, int part_world) {
-    if (!cam || part_world < 1 || part_rank < 0 || part_rank >= part_world) return -1;
-    return part_tiles(geom(cam, part_world), part_rank, part_world);
+// ---- partition bookkeeping ------------------------------------------------------------------------------------
+
+int rt_band_height(const RtCamera *cam, int aa, int part_world) {
+    if (!cam || part_world < 1 || aa < 1) return -1;
+    return item_geometry(cam, aa, part_world).Ph;
 }
 
-int64_t rt_part_bytes(const RtCamera *cam, int part_rank, int part_world) {
-    int64_t t = rt_part_tiles(cam, part_rank, part_world);
-    return t < 0 ? t : t * RT_TILE * RT_TILE * 3;
+int64_t rt_part_rows(const RtCamera *cam, int aa, int part_rank, int part_world) {
+    if (!cam || part_world < 1 || part_rank < 0 || part_rank >= part_world || aa < 1) return -1;
+    const ItemGeom g = item_geometry(cam, aa, part_world);
+    return part_bands(g, part_rank, part_world) * g.Ph;  // the last band is padded to the full band height
+}
+
+int64_t rt_part_bytes(const RtCamera *cam, int aa, int part_rank, int part_world) {
+    const int64_t rows = rt_part_rows(cam, aa, part_rank, part_world);
+    return rows < 0 ? rows : rows * cam->image_width * 3;
+}
+
+// ---- rendering ------------------------------------------------------------------------------------------------
+
+int rt_render_async(RtScene *s, const RtCamera *cam, int aa, unsigned char *rgb_out, int *ticket) {
+    int rc = check_render_args(s, cam, aa, 0, 1);
+    if (rc != RT_OK) return rc;
+    if (!rgb_out || !ticket) return fail(RT_ERR_INVALID, "rgb_out or ticket is NULL");
+    DeviceGuard g;
+    if (g.use(s->device) != 0) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
+    const int k = (int) (s->next_ticket % kFrameSlots);
+    RenderSlot &sl = s->slot[k];
+    if (sl.busy) return fail(RT_ERR_STATE, "too many frames in flight on this handle (rt_wait the oldest first)");
+    rc = slot_prepare(sl);
+    if (rc != RT_OK) return rc;
+    const size_t bytes = (size_t) cam->image_width * cam->image_height * 3;
+    rc = ensure(&sl.d_frame, &sl.frame_cap, bytes, false);
+    if (rc != RT_OK) return rc;
+    sl.launches = 0;
+    CU(cudaEventRecord(sl.ev_start, s->stream));
+    rc = enqueue_part(s, cam, aa, 0, 1, sl.d_frame, kOutFrame, k, s->stream, &sl.launches);
+    if (rc != RT_OK) return rc;
+    CU(cudaEventRecord(sl.ev_kernel, s->stream));
+    // while the kernel runs: make sure there is page-locked memory to copy into
+    const bool pinned_dst = is_pinned(rgb_out);
+    if (!pinned_dst) {
+        rc = ensure(&sl.h_pinned, &sl.pinned_cap, bytes, true);
+        if (rc != RT_OK) return rc;
+    }
+    // the copies go to a second stream so that the next frame's kernel does not queue behind this frame's D2H
+    CU(cudaStreamWaitEvent(s->copy_stream, sl.ev_kernel, 0));
+    CU(cudaMemcpyAsync(pinned_dst ? rgb_out : sl.h_pinned, sl.d_frame, bytes, cudaMemcpyDeviceToHost, s->copy_stream));
+    CU(cudaMemcpyAsync(sl.h_stats, s->buf.control + 8 * k, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->copy_stream));
+    CU(cudaEventRecord(sl.ev_done, s->copy_stream));
+    sl.busy = true;
+    sl.dst = rgb_out;
+    sl.bytes = bytes;
+    sl.staged = !pinned_dst;
+    *ticket = (int) s->next_ticket;
+    s->next_ticket++;
+    return RT_OK;
+}
+
+int rt_wait(RtScene *s, int ticket, RtStats *stats) {
+    if (!s) return fail(RT_ERR_INVALID, "NULL scene");
+    RenderSlot &sl = s->slot[(unsigned) ticket % kFrameSlots];
+    if (!sl.busy) return fail(RT_ERR_STATE, "no frame in flight under this ticket");
+    DeviceGuard g;
+    if (g.use(s->device) != 0) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
+    sl.busy = false;
+    CU(cudaEventSynchronize(sl.ev_done));
+    if (sl.staged) memcpy(sl.dst, sl.h_pinned, sl.bytes);
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats_from_words(sl.h_stats, stats);
+        cudaEventElapsedTime(&stats->ms_render, sl.ev_start, sl.ev_kernel);
+        cudaEventElapsedTime(&stats->ms_total, sl.ev_start, sl.ev_done);
+        stats->ms_d2h = stats->ms_total - stats->ms_render;
+        stats->n_launches = sl.launches;
+    }
+    return RT_OK;
 }
 
 int rt_render(RtScene *s, const RtCamera *cam, int aa, unsigned char *rgb_out, RtStats *stats) {
-    int rc = check_render_args(s, cam, aa, 0, 1);
+    int ticket = 0;
+    int rc = rt_render_async(s, cam, aa, rgb_out, &ticket);
     if (rc != RT_OK) return rc;
-    if (!rgb_out) return fail(RT_ERR_INVALID, "rgb_out is NULL");
-    const size_t bytes = (size_t) cam->image_width * cam->image_height * 3;
-    rc = ensure(&s->d_frame, &s->frame_cap, bytes, false);
-    if (rc != RT_OK) return rc;
-    cudaPointerAttributes attr;
-    bool pinned_dst = cudaPointerGetAttributes(&attr, rgb_out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-    cudaGetLastError();
-    if (!pinned_dst) {
-        rc = ensure(&s->h_pinned, &s->pinned_cap, bytes, true);
-        if (rc != RT_OK) return rc;
-    }
-    int launches = 0;
-    CU(cudaEventRecord(s->ev[0], s->stream));
-    rc = enqueue_part(s, cam, aa, 0, 1, s->d_frame, kOutFrame, s->stream, &launches);
-    if (rc != RT_OK) return rc;
-    CU(cudaEventRecord(s->ev[1], s->stream));
-    CU(cudaMemcpyAsync(pinned_dst ? rgb_out : s->h_pinned, s->d_frame, bytes, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaEventRecord(s->ev[2], s->stream));
-    CU(cudaStreamSynchronize(s->stream));
-    if (!pinned_dst) memcpy(rgb_out, s->h_pinned, bytes);
-    if (stats) {
-        memset(stats, 0, sizeof *stats);
-        rc = fetch_stats(s, stats);
-        if (rc != RT_OK) return rc;
-        cudaEventElapsedTime(&stats->ms_render, s->ev[0], s->ev[1]);
-        cudaEventElapsedTime(&stats->ms_d2h, s->ev[1], s->ev[2]);
-        cudaEventElapsedTime(&stats->ms_total, s->ev[0], s->ev[2]);
-        stats->n_launches = launches;
-    }
-    return RT_OK;
+    return rt_wait(s, ticket, stats);
 }
 
-static int render_part_common(RtScene *s, const RtCamera *cam, int aa, int rank, int world, void *d_out, int mode,
-                              void *cuda_stream, RtStats *stats) {
-    int rc = check_render_args(s, cam, aa, rank, world);
-    if (rc != RT_OK) return rc;
-    if (!d_out) return fail(RT_ERR_INVALID, "device output pointer is NULL");
-    cudaStream_t st = (cudaStream_t) cuda_stream;
-    int launches = 0;
-    if (stats) CU(cudaEventRecord(s->ev[0], st));
-    rc = enqueue_part(s, cam, aa, rank, world, (unsigned char *) d_out, mode, st, &launches);
-    if (rc != RT_OK) return rc;
-    if (stats) {
-        CU(cudaEventRecord(s->ev[1], st));
-        CU(cudaStreamSynchronize(st));
-        memset(stats, 0, sizeof *stats);
-        rc = fetch_stats(s, stats);
-        if (rc != RT_OK) return rc;
-        cudaEventElapsedTime(&stats->ms_render, s->ev[0], s->ev[1]);
-        stats->ms_total = stats->ms_render;
-        stats->n_launches = launches;
-    }
-    return RT_OK;
-}
-
-int rt_render_part(RtScene *s, const RtCamera *cam, int aa, int rank, int world, void *d_tiles, void *cuda_stream,
+int rt_render_part(RtScene *s, const RtCamera *cam, int aa, int rank, int world, void *d_rows, void *cuda_stream,
                    RtStats *stats) {
-    return render_part_common(s, cam, aa, rank, world, d_tiles, kOutPacked, cuda_stream, stats);
+    return render_part_common(s, cam, aa, rank, world, d_rows, kOutPacked, cuda_stream, stats);
 }
 
 int rt_render_part_into_frame(RtScene *s, const RtCamera *cam, int aa, int rank, int world, void *d_frame,
@@ -862,14 +894,37 @@ int rt_render_part_into_frame(RtScene *s, const RtCamera *cam, int aa, int rank,
     return render_part_common(s, cam, aa, rank, world, d_frame, kOutFrame, cuda_stream, stats);
 }
 
-int rt_assemble_tiles(const RtCamera *cam, int part_world, const void *d_parts, int64_t part_stride_bytes, void *d_frame,
+int rt_assemble_parts(const RtCamera *cam, int aa, int part_world, const void *d_parts, int64_t part_stride_bytes, void *d_frame,
                       void *cuda_stream) {
-    if (!cam || !d_parts || !d_frame || part_world < 1) return fail(RT_ERR_INVALID, "bad argument");
-    const FrameGeom g = geom(cam, part_world);
+    if (!cam || !d_parts || !d_frame || part_world < 1 || aa < 1) return fail(RT_ERR_INVALID, "bad argument");
+    const ItemGeom g = item_geometry(cam, aa, part_world);
     cudaError_t e = (cudaError_t) launch_assemble((const unsigned char *) d_parts, part_stride_bytes, part_world, cam->image_width,
-                                                  cam->image_height, g.tiles_x, g.n_tiles, (unsigned char *) d_frame,
-                                                  (cudaStream_t) cuda_stream);
+                                                  cam->image_height, g.Ph, (unsigned char *) d_frame, (cudaStream_t) cuda_stream);
     if (e != cudaSuccess) return fail(RT_ERR_CUDA, std::string("assemble kernel launch: ") + cudaGetErrorString(e));
+    return RT_OK;
+}
+
+int rt_render_part_to_host(RtScene *s, const RtCamera *cam, int aa, int rank, int world, unsigned char *host_frame, RtStats *stats) {
+    int rc = check_render_args(s, cam, aa, rank, world);
+    if (rc != RT_OK) return rc;
+    if (!host_frame) return fail(RT_ERR_INVALID, "host_frame is NULL");
+    DeviceGuard g;
+    if (g.use(s->device) != 0) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
+    const double t0 = now_ms();
+    int launches = 0;
+    rc = enqueue_part_to_host(s, cam, aa, rank, world, host_frame, &launches);
+    if (rc != RT_OK) return rc;
+    unsigned long long h[8];
+    CU(cudaMemcpyAsync(h, s->buf.control + 8 * (kControlSlots - 1), sizeof h, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats_from_words(h, stats);
+        cudaEventElapsedTime(&stats->ms_render, s->ev_part[0], s->ev_part[1]);
+        stats->ms_total = (float) (now_ms() - t0);
+        stats->ms_d2h = stats->ms_total - stats->ms_render;
+        stats->n_launches = launches;
+    }
     return RT_OK;
 }
 
@@ -881,71 +936,56 @@ int rt_render_multi(RtScene *const *scenes, int n, const RtCamera *cam, int aa, 
         if (rc != RT_OK) return rc;
     }
     if (!rgb_out) return fail(RT_ERR_INVALID, "rgb_out is NULL");
+    DeviceGuard g;
     RtScene *root = scenes[0];
     const size_t bytes = (size_t) cam->image_width * cam->image_height * 3;
-    const int64_t stride = rt_part_bytes(cam, 0, n);  // part 0 owns the most tiles
-    int prev = 0;
-    cudaGetDevice(&prev);
+    const double t0 = now_ms();
+    // every GPU copies its own bands over its own PCIe link straight into the caller's frame (page-locked), or into
+    // the root handle's page-locked staging frame when the caller's memory is pageable
+    unsigned char *frame = rgb_out;
+    const bool pinned_dst = is_pinned(rgb_out);
+    if (!pinned_dst) {
+        if (g.use(root->device) != 0) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
+        int rc = ensure(&root->slot[0].h_pinned, &root->slot[0].pinned_cap, bytes, true);
+        if (rc != RT_OK) return rc;
+        frame = root->slot[0].h_pinned;
+    }
     int launches = 0;
-    // per-device packed buffers (reuse d_frame of each handle), gather buffer on the root
-    CU(cudaSetDevice(root->device));
-    int rc = ensure(&root->d_parts, &root->parts_cap, (size_t) stride * n, false);
-    if (rc == RT_OK) rc = ensure(&root->d_frame, &root->frame_cap, bytes, false);
-    if (rc == RT_OK) rc = ensure(&root->h_pinned, &root->pinned_cap, bytes, true);
-    if (rc != RT_OK) return rc;
-    CU(cudaEventRecord(root->ev[0], root->stream));
+    for (int i = 0; i < n; i++) {
+        if (g.use(scenes[i]->device) != 0) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
+        int rc = enqueue_part_to_host(scenes[i], cam, aa, i, n, frame, &launches);
+        if (rc != RT_OK) return rc;
+    }
+    float ms_render = 0;
+    if (stats) memset(stats, 0, sizeof *stats);
     for (int i = 0; i < n; i++) {
         RtScene *s = scenes[i];
-        CU(cudaSetDevice(s->device));
-        unsigned char *dst;
-        if (i == 0) {
-            dst = root->d_parts;
-        } else {
-            rc = ensure(&s->d_frame, &s->frame_cap, (size_t) stride, false);
-            if (rc != RT_OK) return rc;
-            dst = s->d_frame;
-        }
-        rc = enqueue_part(s, cam, aa, i, n, dst, kOutPacked, s->stream, &launches);
-        if (rc != RT_OK) return rc;
-        if (i != 0) {
-            // one peer copy per GPU over NVLink, ordered after that GPU's render
-            CU(cudaMemcpyPeerAsync(root->d_parts + (size_t) stride * i, root->device, s->d_frame, s->device,
-                                   (size_t) rt_part_bytes(cam, i, n), s->stream));
-            CU(cudaEventRecord(s->ev[3], s->stream));
-        }
-    }
-    CU(cudaSetDevice(root->device));
-    for (int i = 1; i < n; i++) CU(cudaStreamWaitEvent(root->stream, scenes[i]->ev[3], 0));
-    CU(cudaEventRecord(root->ev[1], root->stream));
-    rc = rt_assemble_tiles(cam, n, root->d_parts, stride, root->d_frame, root->stream);
-    if (rc != RT_OK) return rc;
-    launches++;
-    CU(cudaMemcpyAsync(root->h_pinned, root->d_frame, bytes, cudaMemcpyDeviceToHost, root->stream));
-    CU(cudaEventRecord(root->ev[2], root->stream));
-    CU(cudaStreamSynchronize(root->stream));
-    memcpy(rgb_out, root->h_pinned, bytes);
-    if (stats) {
-        memset(stats, 0, sizeof *stats);
-        for (int i = 0; i < n; i++) {
+        if (g.use(s->device) != 0) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
+        unsigned long long h[8];
+        CU(cudaMemcpyAsync(h, s->buf.control + 8 * (kControlSlots - 1), sizeof h, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        if (stats) {
             RtStats part;
             memset(&part, 0, sizeof part);
-            CU(cudaSetDevice(scenes[i]->device));
-            rc = fetch_stats(scenes[i], &part);
-            if (rc != RT_OK) return rc;
+            stats_from_words(h, &part);
             stats->primary_rays += part.primary_rays;
             stats->reflection_rays += part.reflection_rays;
             stats->shadow_rays += part.shadow_rays;
             stats->shadow_occluded += part.shadow_occluded;
             stats->replayed_closest += part.replayed_closest;
             stats->replayed_any += part.replayed_any;
+            float ms = 0;
+            cudaEventElapsedTime(&ms, s->ev_part[0], s->ev_part[1]);
+            ms_render = std::max(ms_render, ms);
         }
-        CU(cudaSetDevice(root->device));
-        cudaEventElapsedTime(&stats->ms_render, root->ev[0], root->ev[1]);
-        cudaEventElapsedTime(&stats->ms_d2h, root->ev[1], root->ev[2]);
-        cudaEventElapsedTime(&stats->ms_total, root->ev[0], root->ev[2]);
+    }
+    if (!pinned_dst) memcpy(rgb_out, frame, bytes);
+    if (stats) {
+        stats->ms_render = ms_render;  // the slowest GPU's kernel
+        stats->ms_total = (float) (now_ms() - t0);
+        stats->ms_d2h = stats->ms_total - ms_render;
         stats->n_launches = launches;
     }
-    cudaSetDevice(prev);
     return RT_OK;
 }
 

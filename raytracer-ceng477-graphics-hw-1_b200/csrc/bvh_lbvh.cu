@@ -1,6 +1,6 @@
 // bvh_lbvh.cu — BVH build on the GPU (replaces BVHNode::build / BVHTree::build, bvh.h:48-178).
 //
-//   1. centroid bounds            (block reduction + ordered-int atomics)
+//   1. centroid bounds            (ordered-int atomics in the per-primitive pre-pass, scene_build.cu)
 //   2. 30-bit Morton code per primitive, key = code << 32 | index (unique keys)
 //   3. bitonic sort of the 64-bit keys (shared-memory stages fused, global stages one launch each)
 //   4. Karras 2012 radix tree: one thread per internal node finds its range and split by binary
@@ -14,56 +14,22 @@
 // reference-order ranks, so nothing here needs to mimic the reference's midpoint splits.
 #include <cfloat>
 #include <cstdint>
-#include <cstdlib>
-#include <vector>
 
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
-#include "rt_internal.h"
+#include "build_device.h"
+
+namespace cg = cooperative_groups;
 
 namespace rtb {
 
 namespace {
 
-constexpr float kCostNode = 1.0f;  // keep in sync with bvh_host.cpp
-constexpr float kCostPrim = 1.6f;
+constexpr float kCostNode = kSahCostNode;
+constexpr float kCostPrim = kSahCostPrim;
 
-__device__ __forceinline__ unsigned ordered(float f) {
-    unsigned u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float unordered(unsigned u) {
-    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
-}
-
-// [0..2] = min (ordered uint), [3..5] = max
-__global__ void centroid_bounds_kernel(const Aabb *bounds, int n, unsigned *out) {
-    __shared__ unsigned smin[3][256], smax[3][256];
-    unsigned mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0u, 0u, 0u};
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const Aabb b = bounds[i];
-        for (int k = 0; k < 3; k++) {
-            unsigned c = ordered(0.5f * (b.mn[k] + b.mx[k]));
-            mn[k] = min(mn[k], c);
-            mx[k] = max(mx[k], c);
-        }
-    }
-    for (int k = 0; k < 3; k++) smin[k][threadIdx.x] = mn[k], smax[k][threadIdx.x] = mx[k];
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if (threadIdx.x < s)
-            for (int k = 0; k < 3; k++) {
-                smin[k][threadIdx.x] = min(smin[k][threadIdx.x], smin[k][threadIdx.x + s]);
-                smax[k][threadIdx.x] = max(smax[k][threadIdx.x], smax[k][threadIdx.x + s]);
-            }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0)
-        for (int k = 0; k < 3; k++) {
-            atomicMin(&out[k], smin[k][0]);
-            atomicMax(&out[3 + k], smax[k][0]);
-        }
-}
+__device__ __forceinline__ float unordered(unsigned u) { return ord2f(u); }
 
 __device__ __forceinline__ unsigned expand10(unsigned v) {  // 10 bits -> every third bit
     v = (v * 0x00010001u) & 0xFF0000FFu;
@@ -305,21 +271,26 @@ __global__ void emit_kernel(const unsigned long long *keys, const Aabb *bounds, 
 }
 
 // ---- PLOC: parallel locally-ordered clustering (Meister & Bittner 2018) on the Morton-sorted primitives --------
-// One CTA of 1024 threads (the shipped scenes have <= 32 K primitives; the build is a one-off per scene):
-// every round, each cluster looks `kPlocRadius` neighbours left and right in the current (Morton) order for the
-// partner whose merged box has the smallest area; mutual nearest neighbours merge into a new node; the cluster
-// list is compacted with a block-wide prefix sum.  SAH cost / leaf collapse are evaluated when a node is
-// created (children always exist already); DFS positions are then pushed down batch by batch so that every
-// subtree owns a contiguous range of the final primitive order.
-constexpr int kPlocRadiusDefault = 16;
-constexpr float kPlocLeafCost = 1.0f;  // per-primitive cost in the collapse decision (tools/ploc_tune.py: 1.0 beats 1.6 and 2.5)
+// Every round, each cluster looks `radius` neighbours left and right in the current (Morton) order for the partner
+// whose merged box has the smallest area; mutual nearest neighbours merge into a new node; the cluster list is
+// compacted in order.  One COOPERATIVE launch runs all rounds: the clusters are dealt in contiguous chunks to the
+// CTAs of the grid, the compaction offsets come from a per-CTA total plus a block-wide scan, and the phases of a
+// round are separated by grid barriers (3 per round); once at most kPlocTail clusters are left, CTA 0 finishes alone
+// with block barriers.  SAH cost / leaf collapse are evaluated when a node is created (children always exist
+// already).  A second, ordinary kernel then gives every leaf its depth-first position by walking up the parent
+// links (subtree sizes are known), which makes every subtree own a contiguous range of the final primitive order.
+// The globally closest pair is always mutual (ties go to the lower index on both sides), so every round merges at
+// least one pair; a chain-like input that needs more than kPlocMaxRounds rounds raises the status flag and the caller
+// falls back to the top-down builder.
 constexpr int kPlocThreads = 1024;
+constexpr int kPlocTail = 2048;
+constexpr int kPlocMaxRounds = 4096;
 
 struct PlocNode {
     Aabb box;
     int left, right;   // node ids; leaves are ids 0..n-1 (sorted position), internal ids n..2n-2
     int size;          // primitives below
-    int first;         // DFS position of the leftmost primitive
+    int parent;        // -1: root
     float cost;
     int collapsed;
 };
@@ -343,32 +314,42 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *smem, int &total
 
 __global__ void __launch_bounds__(kPlocThreads, 1)
 ploc_kernel(const unsigned long long *keys, const Aabb *bounds, int n, PlocNode *nodes, int *cl_a, int *cl_b, int *nn,
-            int *batch_start, int *n_batches_out, HostNode *out, int *prim_order, int do_collapse, int kPlocRadius,
-            float cost_prim) {
+            int *cta_tot, int *state, int *status, int do_collapse, int radius, float cost_prim) {
     __shared__ int scan[kPlocThreads];
-    const int t = threadIdx.x;
-    for (int i = t; i < n; i += kPlocThreads) {
+    cg::grid_group grid = cg::this_grid();
+    const int t = threadIdx.x, G = gridDim.x, cta = blockIdx.x;
+    for (int i = cta * kPlocThreads + t; i < n; i += G * kPlocThreads) {
         PlocNode nd;
         nd.box = bounds[(unsigned) keys[i]];
         nd.left = nd.right = -1;
         nd.size = 1;
-        nd.first = 0;
+        nd.parent = -1;
         nd.cost = cost_prim;
         nd.collapsed = 0;
         nodes[i] = nd;
         cl_a[i] = i;
     }
-    __syncthreads();
-    int m = n, n_alloc = n, n_batches = 0;
+    if (G > 1) grid.sync();
+    else __syncthreads();
+    int m = n, n_alloc = n, rounds = 0;
     int *cin = cl_a, *cout = cl_b;
-    while (m > 1) {
-        if (t == 0) batch_start[n_batches] = n_alloc;
+    bool alone = G == 1;  // CTA 0 finishing the tail (or a single-CTA launch)
+    while (m > 1 && rounds < kPlocMaxRounds) {
+        if (!alone && m <= kPlocTail) {  // hand the tail over to CTA 0 (uniform decision: m is the same in every CTA)
+            alone = true;
+            if (cta != 0) break;
+        }
+        const int ctas = alone ? 1 : G;
+        const int my_cta = alone ? 0 : cta;
+        // this CTA's contiguous chunk of the cluster list, and this thread's contiguous piece of it
+        const int per_cta = (m + ctas - 1) / ctas;
+        const int c0 = min(m, my_cta * per_cta), c1 = min(m, c0 + per_cta);
         // 1. nearest neighbour within the radius (merged half-area), ties to the lower index
-        for (int i = t; i < m; i += kPlocThreads) {
+        for (int i = c0 + t; i < c1; i += kPlocThreads) {
             const Aabb bi = nodes[cin[i]].box;
             float best = FLT_MAX;
             int bj = -1;
-            const int lo = max(0, i - kPlocRadius), hi = min(m - 1, i + kPlocRadius);
+            const int lo = max(0, i - radius), hi = min(m - 1, i + radius);
             for (int j = lo; j <= hi; j++) {
                 if (j == i) continue;
                 const float a = half_area(merge(bi, nodes[cin[j]].box));
@@ -376,10 +357,11 @@ ploc_kernel(const unsigned long long *keys, const Aabb *bounds, int n, PlocNode 
             }
             nn[i] = bj;
         }
-        __syncthreads();
+        if (alone) __syncthreads();
+        else grid.sync();
         // 2. mutual pairs merge (the lower index keeps the slot); count new nodes and surviving clusters
-        const int per = (m + kPlocThreads - 1) / kPlocThreads;
-        const int b0 = min(m, t * per), b1 = min(m, b0 + per);
+        const int per = (c1 - c0 + kPlocThreads - 1) / kPlocThreads;
+        const int b0 = min(c1, c0 + t * per), b1 = min(c1, b0 + per);
         int my_new = 0, my_keep = 0;
         for (int i = b0; i < b1; i++) {
             const int j = nn[i];
@@ -390,6 +372,20 @@ ploc_kernel(const unsigned long long *keys, const Aabb *bounds, int n, PlocNode 
         int tot_new, tot_keep;
         int off_new = block_exclusive_scan(my_new, scan, tot_new);
         int off_keep = block_exclusive_scan(my_keep, scan, tot_keep);
+        int all_new = tot_new, all_keep = tot_keep;
+        if (!alone) {
+            if (t == 0) cta_tot[2 * cta] = tot_new, cta_tot[2 * cta + 1] = tot_keep;
+            grid.sync();
+            all_new = all_keep = 0;
+            int before_new = 0, before_keep = 0;
+            for (int g = 0; g < G; g++) {  // G <= a few hundred: every thread sums the same values
+                const int a = cta_tot[2 * g], b = cta_tot[2 * g + 1];
+                if (g < cta) before_new += a, before_keep += b;
+                all_new += a, all_keep += b;
+            }
+            off_new += before_new;
+            off_keep += before_keep;
+        }
         for (int i = b0; i < b1; i++) {
             const int j = nn[i];
             const bool mutual = j >= 0 && nn[j] == i;
@@ -403,7 +399,7 @@ ploc_kernel(const unsigned long long *keys, const Aabb *bounds, int n, PlocNode 
                 nd.left = l;
                 nd.right = r;
                 nd.size = nl.size + nr.size;
-                nd.first = 0;
+                nd.parent = -1;
                 const float a = half_area(nd.box);
                 float c_split = kCostNode + (a > 0.0f ? (half_area(nl.box) * nl.cost + half_area(nr.box) * nr.cost) / a : nl.cost + nr.cost);
                 const float c_leaf = cost_prim * (float) nd.size;
@@ -415,170 +411,140 @@ ploc_kernel(const unsigned long long *keys, const Aabb *bounds, int n, PlocNode 
                 nd.cost = c_split;
                 id = n_alloc + off_new++;
                 nodes[id] = nd;
+                nodes[l].parent = id;
+                nodes[r].parent = id;
             }
             cout[off_keep++] = id;
         }
-        __syncthreads();
-        n_alloc += tot_new;
-        m = tot_keep;
-        n_batches++;
+        n_alloc += all_new;
+        m = all_keep;
+        rounds++;
         int *tmp = cin;
         cin = cout;
         cout = tmp;
-        __syncthreads();
+        if (alone) __syncthreads();
+        else grid.sync();
     }
-    const int root = cin[0];  // == n_alloc - 1 == 2n - 2
-    if (t == 0) {
-        batch_start[n_batches] = n_alloc;
-        *n_batches_out = n_batches;
-        nodes[root].first = 0;
-        nodes[root].collapsed = 0;  // node 0 of the traversal tree must be an inner node
-    }
-    __syncthreads();
-    // 3. DFS positions, top-down, one creation batch at a time (children are always older than their parent)
-    for (int b = n_batches - 1; b >= 0; b--) {
-        for (int id = batch_start[b] + t; id < batch_start[b + 1]; id += kPlocThreads) {
-            const PlocNode nd = nodes[id];
-            nodes[nd.left].first = nd.first;
-            nodes[nd.right].first = nd.first + nodes[nd.left].size;
-        }
-        __syncthreads();
-    }
-    for (int i = t; i < n; i += kPlocThreads) prim_order[nodes[i].first] = (int) (unsigned) keys[i];
-    // 4. emit the 64-byte traversal nodes: internal id -> index (2n-2 - id), so the root lands at 0
-    for (int id = n + t; id < 2 * n - 1; id += kPlocThreads) {
-        const PlocNode nd = nodes[id];
-        HostNode h;
-        const int ch[2] = {nd.left, nd.right};
-        for (int c = 0; c < 2; c++) {
-            const PlocNode cn = nodes[ch[c]];
-            int ref;
-            if (ch[c] < n) ref = ~((cn.first << 3) | 0);
-            else if (cn.collapsed) ref = ~((cn.first << 3) | (cn.size - 1));
-            else ref = (2 * n - 2) - ch[c];
-            for (int k = 0; k < 3; k++) {
-                if (c == 0) h.c0mn[k] = cn.box.mn[k], h.c0mx[k] = cn.box.mx[k];
-                else h.c1mn[k] = cn.box.mn[k], h.c1mx[k] = cn.box.mx[k];
-            }
-            if (c == 0) h.child0 = ref;
-            else h.child1 = ref;
-        }
-        out[(2 * n - 2) - id] = h;
+    if (cta == 0 && t == 0) {
+        state[0] = m;
+        state[1] = n_alloc;
+        state[2] = rounds;
+        state[3] = cin[0];  // the root when m == 1 (== 2n - 2)
+        *status = m > 1 ? 1 : 0;
+        if (m == 1) nodes[cin[0]].collapsed = 0;  // node 0 of the traversal tree must be an inner node
     }
 }
 
-#define CK(call)                         \
-    do {                                 \
-        if ((call) != cudaSuccess) {     \
-            cleanup();                   \
-            return -1;                   \
-        }                                \
-    } while (0)
+// depth-first position of every leaf (walk up: add the left sibling's size whenever the path comes from the right),
+// then the traversal nodes: internal id -> index (2n-2 - id), so the root lands at 0
+__global__ void ploc_order_kernel(const unsigned long long *keys, int n, const PlocNode *nodes, int *first_of, int *prim_order,
+                                  const int *status) {
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= 2 * n - 1 || *status != 0) return;
+    // position of the leftmost leaf below `id`
+    int pos = 0, cur = id;
+    for (int guard = 0; guard < (1 << 22); guard++) {
+        const int par = nodes[cur].parent;
+        if (par < 0) break;
+        if (nodes[par].right == cur) pos += nodes[nodes[par].left].size;
+        cur = par;
+    }
+    first_of[id] = pos;
+    if (id < n) prim_order[pos] = (int) (unsigned) keys[id];
+}
+
+__global__ void ploc_emit_kernel(int n, const PlocNode *nodes, const int *first_of, HostNode *out, const int *status) {
+    const int id = n + blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= 2 * n - 1 || *status != 0) return;
+    const PlocNode nd = nodes[id];
+    HostNode h;
+    const int ch[2] = {nd.left, nd.right};
+    for (int c = 0; c < 2; c++) {
+        const PlocNode cn = nodes[ch[c]];
+        const int first = first_of[ch[c]];
+        int ref;
+        if (ch[c] < n) ref = ~((first << 3) | 0);
+        else if (cn.collapsed) ref = ~((first << 3) | (cn.size - 1));
+        else ref = (2 * n - 2) - ch[c];
+        for (int k = 0; k < 3; k++) {
+            if (c == 0) h.c0mn[k] = cn.box.mn[k], h.c0mx[k] = cn.box.mx[k];
+            else h.c1mn[k] = cn.box.mn[k], h.c1mx[k] = cn.box.mx[k];
+        }
+        if (c == 0) h.child0 = ref;
+        else h.child1 = ref;
+    }
+    out[(2 * n - 2) - id] = h;
+}
+
+__global__ void lbvh_order_kernel(const unsigned long long *keys, int n, int *prim_order, int *status) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) prim_order[i] = (int) (unsigned) keys[i];
+    if (i == 0) *status = 0;
+}
 
 }  // namespace
 
-int build_bvh_device(const std::vector<Aabb> &bounds, HostBvh &out, float *ms_device, int use_ploc) {
-    out = HostBvh();
-    const int n = (int) bounds.size();
-    if (n == 0) return 0;
-    if (n == 1) {  // a single leaf under a root node
-        HostNode nd;
-        for (int k = 0; k < 3; k++) {
-            nd.c0mn[k] = bounds[0].mn[k], nd.c0mx[k] = bounds[0].mx[k];
-            nd.c1mn[k] = FLT_MAX, nd.c1mx[k] = -FLT_MAX;
-        }
-        nd.child0 = ~0;
-        nd.child1 = kEmptyChild;
-        out.nodes.push_back(nd);
-        out.prim_order = {0};
-        return 0;
-    }
+int morton_pad(int n) {
     int n_pad = 1;
     while (n_pad < n) n_pad <<= 1;
     if (n_pad < kSortTile) n_pad = kSortTile;
+    return n_pad;
+}
 
-    Aabb *d_bounds = nullptr, *d_box = nullptr;
-    unsigned *d_cb = nullptr, *d_flags = nullptr;
-    unsigned long long *d_keys = nullptr;
-    TreeNode *d_nodes = nullptr;
-    int *d_leaf_parent = nullptr, *d_collapsed = nullptr;
-    float *d_cost = nullptr;
-    HostNode *d_out = nullptr;
-    PlocNode *d_ploc = nullptr;
-    int *d_cl_a = nullptr, *d_cl_b = nullptr, *d_nn = nullptr, *d_batch = nullptr, *d_order = nullptr;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    auto cleanup = [&]() {
-        cudaFree(d_bounds); cudaFree(d_box); cudaFree(d_cb); cudaFree(d_flags); cudaFree(d_keys); cudaFree(d_nodes);
-        cudaFree(d_leaf_parent); cudaFree(d_collapsed); cudaFree(d_cost); cudaFree(d_out);
-        cudaFree(d_ploc); cudaFree(d_cl_a); cudaFree(d_cl_b); cudaFree(d_nn); cudaFree(d_batch); cudaFree(d_order);
-        if (e0) cudaEventDestroy(e0);
-        if (e1) cudaEventDestroy(e1);
-    };
-    CK(cudaMalloc(&d_bounds, sizeof(Aabb) * n));
-    CK(cudaMalloc(&d_box, sizeof(Aabb) * n));
-    CK(cudaMalloc(&d_cb, sizeof(unsigned) * 6));
-    CK(cudaMalloc(&d_flags, sizeof(unsigned) * n));
-    CK(cudaMalloc(&d_keys, sizeof(unsigned long long) * n_pad));
-    CK(cudaMalloc(&d_nodes, sizeof(TreeNode) * n));
-    CK(cudaMalloc(&d_leaf_parent, sizeof(int) * n));
-    CK(cudaMalloc(&d_collapsed, sizeof(int) * n));
-    CK(cudaMalloc(&d_cost, sizeof(float) * n));
-    CK(cudaMalloc(&d_out, sizeof(HostNode) * n));
-    if (use_ploc) {
-        CK(cudaMalloc(&d_ploc, sizeof(PlocNode) * (2 * (size_t) n)));
-        CK(cudaMalloc(&d_cl_a, sizeof(int) * n));
-        CK(cudaMalloc(&d_cl_b, sizeof(int) * n));
-        CK(cudaMalloc(&d_nn, sizeof(int) * n));
-        CK(cudaMalloc(&d_batch, sizeof(int) * 4096));
-        CK(cudaMalloc(&d_order, sizeof(int) * n));
-    }
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
-    CK(cudaMemcpy(d_bounds, bounds.data(), sizeof(Aabb) * n, cudaMemcpyHostToDevice));
-    const unsigned cb_init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
-    CK(cudaMemcpy(d_cb, cb_init, sizeof cb_init, cudaMemcpyHostToDevice));
-    CK(cudaMemset(d_flags, 0, sizeof(unsigned) * n));
-    CK(cudaMemset(d_collapsed, 0, sizeof(int) * n));
-    CK(cudaMemset(d_nodes, 0xff, sizeof(TreeNode) * n));
-
-    CK(cudaEventRecord(e0));
-    const int T = 256;
-    centroid_bounds_kernel<<<min(148 * 4, (n + T - 1) / T), T>>>(d_bounds, n, d_cb);
-    morton_kernel<<<(n_pad + T - 1) / T, T>>>(d_bounds, n, n_pad, d_cb, d_keys);
-    bitonic_local_kernel<<<n_pad / kSortTile, 1024>>>(d_keys, n_pad);
+void enqueue_morton_sort(const Aabb *bounds, int n, const unsigned *centroid_bounds, const MortonScratch &m, cudaStream_t stream) {
+    const int T = 256, n_pad = m.n_pad;
+    morton_kernel<<<(n_pad + T - 1) / T, T, 0, stream>>>(bounds, n, n_pad, centroid_bounds, m.keys);
+    bitonic_local_kernel<<<n_pad / kSortTile, 1024, 0, stream>>>(m.keys, n_pad);
     for (int k = kSortTile * 2; k <= n_pad; k <<= 1) {
         for (int j = k >> 1; j >= kSortTile; j >>= 1)
-            bitonic_global_kernel<<<(n_pad / 2 + T - 1) / T, T>>>(d_keys, n_pad, j, k);
-        bitonic_merge_local_kernel<<<n_pad / kSortTile, 1024>>>(d_keys, n_pad, k);
+            bitonic_global_kernel<<<(n_pad / 2 + T - 1) / T, T, 0, stream>>>(m.keys, n_pad, j, k);
+        bitonic_merge_local_kernel<<<n_pad / kSortTile, 1024, 0, stream>>>(m.keys, n_pad, k);
     }
-    if (use_ploc) {
-        // tuning knobs for experiments (tools/builder_ab.py): search radius and the leaf cost of the SAH collapse
-        const char *er = getenv("RT_B200_PLOC_RADIUS"), *ec = getenv("RT_B200_PLOC_LEAF_COST");
-        const int radius = er ? atoi(er) : kPlocRadiusDefault;
-        const float cost_prim = ec ? (float) atof(ec) : kPlocLeafCost;
-        ploc_kernel<<<1, kPlocThreads>>>(d_keys, d_bounds, n, d_ploc, d_cl_a, d_cl_b, d_nn, d_batch, d_batch + 4095, d_out, d_order,
-                                         cost_prim < 1e9f, radius, cost_prim);
-    } else {
-        radix_tree_kernel<<<(n - 1 + T - 1) / T, T>>>(d_keys, n, d_nodes, d_leaf_parent);
-        refit_kernel<<<(n + T - 1) / T, T>>>(d_keys, d_bounds, n, d_nodes, d_leaf_parent, d_box, d_cost, d_collapsed, d_flags, 1);
-        emit_kernel<<<(n - 1 + T - 1) / T, T>>>(d_keys, d_bounds, n, d_nodes, d_box, d_collapsed, d_out);
-    }
-    CK(cudaEventRecord(e1));
-    CK(cudaEventSynchronize(e1));
-    CK(cudaGetLastError());
-    if (ms_device) cudaEventElapsedTime(ms_device, e0, e1);
+}
 
-    out.nodes.resize((size_t) n - 1);
-    CK(cudaMemcpy(out.nodes.data(), d_out, sizeof(HostNode) * (n - 1), cudaMemcpyDeviceToHost));
-    std::vector<unsigned long long> keys((size_t) n);
-    CK(cudaMemcpy(keys.data(), d_keys, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost));
-    out.prim_order.resize((size_t) n);
-    if (use_ploc) CK(cudaMemcpy(out.prim_order.data(), d_order, sizeof(int) * n, cudaMemcpyDeviceToHost));
-    else
-        for (int i = 0; i < n; i++) out.prim_order[i] = (int) (unsigned) keys[i];
-    cleanup();
-    out.sah_cost = bvh_sah_cost(out);
-    return 0;
+size_t ploc_node_bytes() { return sizeof(PlocNode); }
+
+int ploc_max_grid(int n_sms) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ploc_kernel, kPlocThreads, 0) != cudaSuccess || per_sm < 1) return 1;
+    return n_sms * per_sm;
+}
+
+int enqueue_ploc(const Aabb *bounds, int n, const MortonScratch &m, const PlocScratch &s, DevTree &out, int radius,
+                 float leaf_cost, int grid, cudaStream_t stream) {
+    // n >= 2.  One CTA per 4096 clusters, at most `grid`; small inputs run as a single CTA without grid barriers.
+    int want = (n + 4095) / 4096;
+    if (want > grid) want = grid;
+    if (want < 1 || n <= kPlocTail) want = 1;
+    const unsigned long long *keys = m.keys;
+    PlocNode *nodes = (PlocNode *) s.nodes;
+    int *cl_a = s.cl_a, *cl_b = s.cl_b, *nn = s.nn, *cta_tot = s.cta_tot, *state = s.state, *status = out.status;
+    int do_collapse = leaf_cost < 1e9f ? 1 : 0;
+    void *args[] = {&keys, &bounds, &n, &nodes, &cl_a, &cl_b, &nn, &cta_tot, &state, &status, &do_collapse, &radius, &leaf_cost};
+    cudaError_t e;
+    if (want > 1) e = cudaLaunchCooperativeKernel((void *) ploc_kernel, dim3(want), dim3(kPlocThreads), args, 0, stream);
+    else e = cudaLaunchKernel((void *) ploc_kernel, dim3(1), dim3(kPlocThreads), args, 0, stream);
+    if (e != cudaSuccess) return (int) e;
+    const int T = 256;
+    // first_of lives in nn's neighbour cl_b? No: both cluster lists are dead now, reuse cl_a ++ cl_b as first_of[2n]
+    int *first_of = s.cl_a;  // cl_a and cl_b are adjacent (scene_build.cu allocates them as one block of 2n ints)
+    ploc_order_kernel<<<(2 * n - 1 + T - 1) / T, T, 0, stream>>>(keys, n, nodes, first_of, out.prim_order, status);
+    ploc_emit_kernel<<<(n - 1 + T - 1) / T, T, 0, stream>>>(n, nodes, first_of, out.nodes, status);
+    return (int) cudaGetLastError();
+}
+
+size_t lbvh_node_bytes() { return sizeof(TreeNode); }
+
+void enqueue_lbvh(const Aabb *bounds, int n, const MortonScratch &m, const LbvhScratch &s, DevTree &out, cudaStream_t stream) {
+    const int T = 256;
+    TreeNode *nodes = (TreeNode *) s.nodes;
+    cudaMemsetAsync(s.flags, 0, sizeof(unsigned) * n, stream);
+    cudaMemsetAsync(s.collapsed, 0, sizeof(int) * n, stream);
+    cudaMemsetAsync(nodes, 0xff, sizeof(TreeNode) * n, stream);
+    radix_tree_kernel<<<(n - 1 + T - 1) / T, T, 0, stream>>>(m.keys, n, nodes, s.leaf_parent);
+    refit_kernel<<<(n + T - 1) / T, T, 0, stream>>>(m.keys, bounds, n, nodes, s.leaf_parent, s.box, s.cost, s.collapsed, s.flags, 1);
+    emit_kernel<<<(n - 1 + T - 1) / T, T, 0, stream>>>(m.keys, bounds, n, nodes, s.box, s.collapsed, out.nodes);
+    lbvh_order_kernel<<<(n + T - 1) / T, T, 0, stream>>>(m.keys, n, out.prim_order, out.status);
 }
 
 }  // namespace rtb

@@ -2,7 +2,8 @@
 //
 // The same algorithm as the host yardstick (bvh_host.cpp: 32 centroid bins per axis, SAH sweep, leaves of at most 8
 // primitives when cheaper, median split when the SAH finds nothing), level-synchronous: one kernel launch per tree
-// level, one CTA per open range.  A CTA reduces the range's bounds and centroid bounds, bins the primitives with
+// level, persistent CTAs striding over the open ranges of the level (their number lives in device memory: no host
+// round trip between levels).  A CTA reduces the range's bounds and centroid bounds, bins the primitives with
 // shared-memory atomics (order-independent: counts and min/max are exact), one thread sweeps the 3 x 31 split
 // candidates in the host's order with the host's float operations (the same decisions, hence the same tree up to
 // the order of primitives inside a leaf), then the CTA partitions the range with a block-wide prefix sum, reduces
@@ -10,26 +11,19 @@
 // RT_BUILD_AUTO choose between two GPU-built trees.
 #include <cfloat>
 #include <cstdint>
-#include <vector>
 
 #include <cuda_runtime.h>
 
-#include "rt_internal.h"
+#include "build_device.h"
 
 namespace rtb {
 
 namespace {
 
 constexpr int kBins = 32;
-constexpr float kCostNode = 1.0f;  // keep in sync with bvh_host.cpp
-constexpr float kCostPrim = 1.6f;
+constexpr float kCostNode = kSahCostNode;
+constexpr float kCostPrim = kSahCostPrim;
 constexpr int kT = 256;
-
-struct SahTask {
-    int parent;  // node that owns the child slot to patch (-1: root)
-    int side;    // 0: child0, 1: child1
-    int lo, hi;
-};
 
 __device__ __forceinline__ unsigned ord(float f) {
     unsigned u = __float_as_uint(f);
@@ -80,19 +74,36 @@ __device__ __forceinline__ int bin_of(const Aabb &pb, int axis, float c0, float 
     return min(kBins - 1, max(0, (int) ((0.5f * (pb.mn[axis] + pb.mx[axis]) - c0) * scale)));
 }
 
-__global__ void __launch_bounds__(kT) sah_level_kernel(const Aabb *bounds, int *ids, int *tmp, const SahTask *tasks, int n_tasks,
-                                                        SahTask *next, int *n_next, HostNode *nodes, int *n_nodes,
-                                                        int *root_ref) {
+__global__ void sah_init_kernel(int n, SahScratch s) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) s.ids[i] = i;
+    if (i == 0) {
+        for (int l = 0; l < kSahLevels + 2; l++) s.level_count[l] = 0;
+        s.level_count[0] = n > 1 ? 1 : 0;
+        s.queue[0][0] = SahTask{-1, 0, 0, n};
+        *s.n_nodes = 0;
+        *s.root_ref = n == 1 ? ~0 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(kT) sah_level_kernel(const Aabb *bounds, SahScratch sc, int level, HostNode *nodes) {
     __shared__ SBox s_box, s_cbox, s_left, s_right;
     __shared__ SBox s_bins[3][kBins];
     __shared__ int s_cnt[3][kBins];
     __shared__ int s_scan[kT];
-    __shared__ int s_axis, s_bin, s_leaf, s_node, s_mid, s_nleft;
+    __shared__ int s_axis, s_bin, s_leaf, s_node;
     __shared__ float s_c0, s_scale;
 
     const int t = threadIdx.x;
-    const SahTask task = tasks[blockIdx.x];
+    const int n_tasks = sc.level_count[level];
+    const SahTask *tasks = sc.queue[level & 1];
+    SahTask *next = sc.queue[(level + 1) & 1];
+    int *n_next = &sc.level_count[level + 1];
+    int *ids = sc.ids, *tmp = sc.tmp, *n_nodes = sc.n_nodes, *root_ref = sc.root_ref;
+  for (int ti = blockIdx.x; ti < n_tasks; ti += gridDim.x) {
+    const SahTask task = tasks[ti];
     const int lo = task.lo, hi = task.hi, n = hi - lo;
+    __syncthreads();  // the previous range's shared state is no longer read
 
     if (t == 0) {
         sbox_reset(s_box);
@@ -168,7 +179,7 @@ __global__ void __launch_bounds__(kT) sah_level_kernel(const Aabb *bounds, int *
         else nodes[task.parent].child1 = ref;
     }
     __syncthreads();
-    if (s_leaf) return;
+    if (s_leaf) continue;
     const int axis = s_axis, me = s_node;
 
     // 4. partition [lo, hi): left = bin <= best bin (order inside the halves is irrelevant to the tree)
@@ -241,94 +252,39 @@ __global__ void __launch_bounds__(kT) sah_level_kernel(const Aabb *bounds, int *
             }
         }
     }
+  }
 }
 
-}  // namespace
-
-int build_bvh_sah_device(const std::vector<Aabb> &bounds, HostBvh &out, float *ms_device) {
-    out = HostBvh();
-    const int n = (int) bounds.size();
-    if (n == 0) return 0;
-    Aabb *d_bounds = nullptr;
-    int *d_ids = nullptr, *d_tmp = nullptr, *d_counters = nullptr;  // counters: [0] n_next, [1] n_nodes, [2] root_ref
-    SahTask *d_q[2] = {nullptr, nullptr};
-    HostNode *d_nodes = nullptr;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    auto cleanup = [&]() {
-        cudaFree(d_bounds); cudaFree(d_ids); cudaFree(d_tmp); cudaFree(d_counters); cudaFree(d_q[0]); cudaFree(d_q[1]); cudaFree(d_nodes);
-        if (e0) cudaEventDestroy(e0);
-        if (e1) cudaEventDestroy(e1);
-    };
-#define CKS(call)                    \
-    do {                             \
-        if ((call) != cudaSuccess) { \
-            cleanup();               \
-            return -1;               \
-        }                            \
-    } while (0)
-    std::vector<int> ids((size_t) n);
-    for (int i = 0; i < n; i++) ids[i] = i;
-    CKS(cudaMalloc(&d_bounds, sizeof(Aabb) * n));
-    CKS(cudaMalloc(&d_ids, sizeof(int) * n));
-    CKS(cudaMalloc(&d_tmp, sizeof(int) * n));
-    CKS(cudaMalloc(&d_counters, sizeof(int) * 4));
-    CKS(cudaMalloc(&d_q[0], sizeof(SahTask) * (size_t) (n + 1)));
-    CKS(cudaMalloc(&d_q[1], sizeof(SahTask) * (size_t) (n + 1)));
-    CKS(cudaMalloc(&d_nodes, sizeof(HostNode) * (size_t) (n + 1)));
-    CKS(cudaEventCreate(&e0));
-    CKS(cudaEventCreate(&e1));
-    CKS(cudaMemcpy(d_bounds, bounds.data(), sizeof(Aabb) * n, cudaMemcpyHostToDevice));
-    CKS(cudaMemcpy(d_ids, ids.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
-    const int counters0[4] = {0, 0, 0, 0};
-    CKS(cudaMemcpy(d_counters, counters0, sizeof counters0, cudaMemcpyHostToDevice));
-    const SahTask root = {-1, 0, 0, n};
-    CKS(cudaMemcpy(d_q[0], &root, sizeof root, cudaMemcpyHostToDevice));
-
-    CKS(cudaEventRecord(e0));
-    int n_tasks = 1, cur = 0;
-    if (n == 1) n_tasks = 0;
-    for (int level = 0; n_tasks > 0 && level < 128; level++) {
-        CKS(cudaMemsetAsync(d_counters, 0, sizeof(int)));
-        sah_level_kernel<<<n_tasks, kT>>>(d_bounds, d_ids, d_tmp, d_q[cur], n_tasks, d_q[cur ^ 1], d_counters, d_nodes,
-                                          d_counters + 1, d_counters + 2);
-        CKS(cudaMemcpy(&n_tasks, d_counters, sizeof(int), cudaMemcpyDeviceToHost));  // one small sync per level
-        cur ^= 1;
-    }
-    CKS(cudaEventRecord(e1));
-    CKS(cudaEventSynchronize(e1));
-    CKS(cudaGetLastError());
-    if (ms_device) cudaEventElapsedTime(ms_device, e0, e1);
-
-    int counters[4];
-    CKS(cudaMemcpy(counters, d_counters, sizeof counters, cudaMemcpyDeviceToHost));
-    const int n_nodes = counters[1], root_ref = n == 1 ? ~0 : counters[2];
-    out.nodes.resize((size_t) n_nodes);
-    if (n_nodes) CKS(cudaMemcpy(out.nodes.data(), d_nodes, sizeof(HostNode) * n_nodes, cudaMemcpyDeviceToHost));
-    out.prim_order.resize((size_t) n);
-    CKS(cudaMemcpy(out.prim_order.data(), d_ids, sizeof(int) * n, cudaMemcpyDeviceToHost));
-    cleanup();
-#undef CKS
-    if (root_ref < 0) {  // the whole scene is one leaf: give it a parent so that node 0 always exists
-        Aabb box = {{FLT_MAX, FLT_MAX, FLT_MAX}, {-FLT_MAX, -FLT_MAX, -FLT_MAX}};
-        for (auto &b: bounds)
-            for (int k = 0; k < 3; k++) box.mn[k] = std::min(box.mn[k], b.mn[k]), box.mx[k] = std::max(box.mx[k], b.mx[k]);
+// the whole scene is one leaf (or one primitive): give it a parent so that node 0 always exists
+__global__ void sah_fixup_kernel(SahScratch s, HostNode *nodes, const BuildResult *res, int *status) {
+    const int root_ref = *s.root_ref;
+    if (root_ref < 0) {
         HostNode nd;
         for (int k = 0; k < 3; k++) {
-            nd.c0mn[k] = box.mn[k], nd.c0mx[k] = box.mx[k];
+            nd.c0mn[k] = ord2f(res->scene_bounds[k]), nd.c0mx[k] = ord2f(res->scene_bounds[3 + k]);
             nd.c1mn[k] = FLT_MAX, nd.c1mx[k] = -FLT_MAX;
         }
         nd.child0 = root_ref;
         nd.child1 = kEmptyChild;
-        out.nodes.assign(1, nd);
-    } else if (root_ref != 0) {
-        std::swap(out.nodes[0], out.nodes[root_ref]);  // cannot happen (the root allocates node 0 first); kept for safety
-        for (auto &nd: out.nodes) {
-            if (nd.child0 == 0) nd.child0 = root_ref; else if (nd.child0 == root_ref) nd.child0 = 0;
-            if (nd.child1 == 0) nd.child1 = root_ref; else if (nd.child1 == root_ref) nd.child1 = 0;
-        }
+        nodes[0] = nd;
+        *s.n_nodes = 1;
     }
-    out.sah_cost = bvh_sah_cost(out);
-    return 0;
+    // still open ranges after the last level: the tree would be deeper than the traversal stack anyway
+    *status = s.level_count[kSahLevels] != 0 ? 1 : 0;
+}
+
+}  // namespace
+
+void enqueue_sah(const Aabb *bounds, int n, const SahScratch &s, DevTree &out, const BuildResult *res, int n_sms,
+                 cudaStream_t stream) {
+    sah_init_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, s);
+    for (int level = 0; level < kSahLevels; level++) {
+        long long open = level < 30 ? (1LL << level) : (1LL << 30);
+        if (open > n) open = n;
+        const long long cap = (long long) n_sms * 8;
+        sah_level_kernel<<<(unsigned) (open < cap ? open : cap), kT, 0, stream>>>(bounds, s, level, out.nodes);
+    }
+    sah_fixup_kernel<<<1, 1, 0, stream>>>(s, out.nodes, res, out.status);
 }
 
 }  // namespace rtb

@@ -27,7 +27,7 @@ void write_ppm(const char *filename, unsigned char *data, int width, int height)
     static const DecTable T;
     FILE *out = fopen(filename, "w");
     if (!out) throw std::runtime_error("Error: The ppm file cannot be opened for writing.");
-    fprintf(out, "P3\n%d %d\n255\n", width, height);
+    bool ok = fprintf(out, "P3\n%d %d\n255\n", width, height) > 0;
     std::vector<char> row((size_t) (width > 0 ? width : 0) * 12 + 2);
     for (int j = 0; j < height; j++) {
         const unsigned char *src = data + (size_t) j * (size_t) width * 3;
@@ -39,7 +39,9 @@ void write_ppm(const char *filename, unsigned char *data, int width, int height)
         }
         if (width > 0) w--;  // the last value of a row carries no trailing space (ppm.cpp:24-27)
         *w++ = '\n';
-        fwrite(row.data(), 1, (size_t) (w - row.data()), out);
+        const size_t n = (size_t) (w - row.data());
+        ok = ok && fwrite(row.data(), 1, n, out) == n;
     }
-    fclose(out);
+    ok = (fclose(out) == 0) && ok;
+    if (!ok) throw std::runtime_error("Error: writing the ppm file failed (disk full?).");
 }

@@ -9,7 +9,7 @@ namespace rtb {
 
 enum OutMode : int {
     kOutFrame = 0,   // row-major RGB8 frame [ny][nx][3] (possibly peer memory)
-    kOutPacked = 1,  // this part's tiles back to back, [local_tile][RT_TILE][RT_TILE][3]
+    kOutPacked = 1,  // this part's row bands back to back, [local_band][band_h][nx][3]
 };
 
 struct RenderParams {
@@ -25,7 +25,7 @@ struct RenderParams {
     const int *ref_leaf_prims;
     const float4 *prim_bounds;      // [2 * n_prims] un-padded bounds of each primitive as the reference computes them
     const int *slot_of_prim;        // prim id -> slot in `prims`
-    int exact_culling;              // 1: reproduce the reference's box-culling decisions (default)
+    int exact_culling;              // 1: reproduce the reference's box-culling decisions (default); 2: replay every hit (tests)
     const float4 *materials;
     const float4 *lights;
     int n_nodes, n_tris, n_prims, n_lights;
@@ -37,21 +37,25 @@ struct RenderParams {
     // camera, precomputed on the host exactly as EyeRayGenerator::init does (raytracer.cpp:292-314)
     float e[3], q[3], u[3], v[3];
     float su_mul, sv_mul;
-    // frame
+    // frame and work decomposition (api.cu item_geometry()): the frame is cut into row bands of band_h = Ph pixel
+    // rows, band b belongs to part b % part_world (the reference deals rows to its threads the same way,
+    // raytracer.cpp:353); a band is cut into items of P x Ph pixels; items are numbered so that consecutive ones
+    // cover a compact ~32 x 32 pixel block (group of `group_bands` bands x column of `tile_items` items)
     int nx, ny;          // output resolution
     int f;               // supersampling factor (sub-sample grid is nx*f by ny*f)
-    int P;               // output pixels per work-item side
-    int Ph;              // work-item height in pixels (= P except on small frames: one 8x4 round per item)
-    int items_x;         // work items per tile row = ceil(RT_TILE / P)
-    int items_y;         // work items per tile column = ceil(RT_TILE / Ph)
-    int tiles_x, tiles_y;
+    int P, Ph;           // item width / height in pixels
+    int items_x;         // items per band = ceil(nx / P)
+    int n_bands;         // bands of this part
+    int group_bands, tile_items, tiles_per_group;
     int part_rank, part_world;
-    unsigned int n_items;  // work items of this part
+    unsigned int n_items;  // work items of this part (incl. empty padding items)
     int out_mode;
-    int refill_threshold;  // kernel 2: refill idle lanes once <= this many lanes are busy
+    int refill_threshold;  // shared-accumulator mode: refill idle lanes once <= this many lanes are busy
+    int acc_mode;          // 0: SSAA sums in warp-private shared memory (any f); 1: in registers (f % 8 == 0), see render_v2.cu
+    int far_camera;        // 1: widen the box test by the ray origin's rounding error (camera far outside the scene)
     unsigned char *out;
-    unsigned int *work_counter;      // zeroed before launch
-    unsigned long long *stats;       // [6] primary, reflection, shadow, occluded, replayed closest, replayed any
+    unsigned long long *control;     // [8]: [0] work counter (zeroed before launch), [1..6] primary, reflection, shadow,
+                                     // occluded, replayed closest, replayed any
 };
 
 }  // namespace rtb

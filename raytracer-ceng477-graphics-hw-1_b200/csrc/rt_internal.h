@@ -18,8 +18,9 @@ namespace rtb {
 //                                    [1] = c1.c.x c1.h.x c1.c.y c1.h.y
 //                                    [2] = c0.c.z c0.h.z c1.c.z c1.h.z
 //                                    [3] = bits(child0) bits(child1) - -
-//                                   child >= 0: inner node index; child < 0: leaf, ~child = (first << 3) | (count - 1)
-//                                   into `prims`; kEmptyChild: no child (box inverted, never hit)
+//                                   child >= 0: inner node as float4 index (4 * node index: the kernel adds it to
+//                                   the base pointer unscaled); child < 0: leaf, ~child = (first << 3) | (count - 1)
+//                                   into `prims`; a missing child is a leaf over the never-hit dummy primitive np
 //  prims      float4[3 * n_prims]   primitives in leaf order (48 B each):
 //                                    triangle [0] = a.x a.y a.z bits(prim_id)      (a = vertex v0)
 //                                             [1] = (a-b).xyz  bits(0)
@@ -33,7 +34,7 @@ namespace rtb {
 //  ranks      uint32[8 * n_prims]   visit rank of prim_id in the reference's traversal order for each
 //                                   ray-direction sign octant (bit a <=> dir[a] > 0) — exact-t tie breaking
 //  ref_nodes  float4[3 * n_ref]     the reference's own tree: [0] = min.xyz bits(axis | is_leaf << 2)
-//                                   [1] = max.xyz bits(right child)  [2] = bits(first) bits(count) - -   (left child = index + 1)
+//                                   [1] = max.xyz bits(left child)  [2] = bits(first) bits(count) - -   (right child = left + 1)
 //  ref_leaf_prims int[n_prims]      prim ids in the reference's leaf order; slot_of_prim int[n_prims]; prim_bounds float4[2 * n_prims]
 //  materials  float4[4 * nm]        [0] = ka.xyz phong  [1] = kd.xyz bits(is_mirror)  [2] = ks.xyz 0  [3] = km.xyz 0
 //  lights     float4[2 * nl]        [0] = position.xyz  [1] = intensity.xyz

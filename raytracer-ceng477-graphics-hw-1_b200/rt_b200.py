@@ -21,7 +21,6 @@ import numpy as np
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 
-RT_TILE = 32
 RT_BUILD_DEFAULT, RT_BUILD_LBVH_GPU, RT_BUILD_SAH_HOST, RT_BUILD_PLOC_GPU, RT_BUILD_AUTO, RT_BUILD_SAH_GPU = 0, 1, 2, 3, 4, 5
 
 
@@ -64,7 +63,8 @@ class RtCamera(C.Structure):
 
 class RtBuildOptions(C.Structure):
     _fields_ = [("builder", C.c_int32), ("brute_force", C.c_int32), ("no_exact_culling", C.c_int32),
-                ("reserved", C.c_int32 * 5)]
+                ("refill_threshold", C.c_int32), ("ploc_radius", C.c_int32), ("ploc_leaf_cost", C.c_float),
+                ("force_replay", C.c_int32), ("reserved", C.c_int32 * 1)]
 
 
 class RtStats(C.Structure):
@@ -83,7 +83,8 @@ class RtSceneInfo(C.Structure):
                 ("bvh_max_depth", C.c_int32), ("ref_tree_nodes", C.c_int32), ("ref_tree_leaves", C.c_int32),
                 ("ref_tree_max_leaf", C.c_int32), ("ref_tree_max_depth", C.c_int32),
                 ("ms_build_host", C.c_float), ("ms_build_device", C.c_float), ("bvh_sah_cost", C.c_float),
-                ("builder", C.c_int32), ("device", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("builder", C.c_int32), ("device", C.c_int32), ("sah_cost_ploc", C.c_float), ("sah_cost_sah", C.c_float),
+                ("ms_create_wall", C.c_float)]
 
 
 class Scene:
@@ -242,15 +243,24 @@ def cuda_lib():
         L.rt_scene_destroy.restype = None
         L.rt_scene_info.argtypes = [C.c_void_p, C.POINTER(RtSceneInfo)]
         L.rt_render.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.c_int, C.c_void_p, C.POINTER(RtStats)]
-        L.rt_part_tiles.restype = C.c_int64
-        L.rt_part_tiles.argtypes = [C.POINTER(RtCamera), C.c_int, C.c_int]
-        L.rt_part_bytes.restype = C.c_int64
-        L.rt_part_bytes.argtypes = [C.POINTER(RtCamera), C.c_int, C.c_int]
+        L.rt_render_async.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+        L.rt_wait.argtypes = [C.c_void_p, C.c_int, C.POINTER(RtStats)]
+        L.rt_host_alloc.argtypes = [C.c_int64, C.POINTER(C.c_void_p)]
+        L.rt_host_free.argtypes = [C.c_void_p]
+        L.rt_band_height.argtypes = [C.POINTER(RtCamera), C.c_int, C.c_int]
+        for fn in ("rt_part_rows", "rt_part_bytes"):
+            getattr(L, fn).restype = C.c_int64
+            getattr(L, fn).argtypes = [C.POINTER(RtCamera), C.c_int, C.c_int, C.c_int]
         for fn in ("rt_render_part", "rt_render_part_into_frame"):
             getattr(L, fn).argtypes = [C.c_void_p, C.POINTER(RtCamera), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                        C.POINTER(RtStats)]
-        L.rt_assemble_tiles.argtypes = [C.POINTER(RtCamera), C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.rt_assemble_parts.argtypes = [C.POINTER(RtCamera), C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.rt_render_part_to_host.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(RtStats)]
+        L.rt_host_frame_create.argtypes = [C.c_char_p, C.c_int64, C.POINTER(C.c_void_p)]
+        L.rt_host_frame_open.argtypes = [C.c_char_p, C.c_int64, C.POINTER(C.c_void_p)]
+        L.rt_host_frame_close.argtypes = [C.c_void_p, C.c_int64, C.c_char_p]
         L.rt_render_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(RtCamera), C.c_int, C.c_void_p, C.POINTER(RtStats)]
+        L.rt_selftest_div3.argtypes = [C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.rt_device_alloc.argtypes = [C.c_int64, C.POINTER(C.c_void_p)]
         L.rt_device_free.argtypes = [C.c_void_p]
         L.rt_ipc_export.argtypes = [C.c_void_p, C.c_char_p]
@@ -265,13 +275,19 @@ def _check(rc):
         raise RtError(f"rt_b200 error {rc}: {cuda_lib().rt_last_error().decode()}")
 
 
+def _host_ptr(out):
+    return out.ctypes.data if isinstance(out, np.ndarray) else out.data_ptr()
+
+
 class RayTracer:
     """RayTracer(scene) / render(camera) — raytracer.cpp:335, :362 — on the current CUDA device."""
 
-    def __init__(self, scene, builder=RT_BUILD_DEFAULT, brute_force=False, exact_culling=True):
+    def __init__(self, scene, builder=RT_BUILD_DEFAULT, brute_force=False, exact_culling=True, refill_threshold=0,
+                 ploc_radius=0, ploc_leaf_cost=0.0, force_replay=False):
         self.L = cuda_lib()
         self.scene = scene
-        opts = RtBuildOptions(builder, 1 if brute_force else 0, 0 if exact_culling else 1)
+        opts = RtBuildOptions(builder, 1 if brute_force else 0, 0 if exact_culling else 1, refill_threshold, ploc_radius, ploc_leaf_cost,
+                              1 if force_replay else 0)
         h = C.c_void_p()
         _check(self.L.rt_scene_create(C.byref(scene.desc), C.byref(opts), C.byref(h)))
         self.h = h
@@ -297,19 +313,30 @@ class RayTracer:
         """Full frame into host memory: HxWx3 uint8 (numpy, or a pinned torch tensor passed as `out`)."""
         if out is None:
             out = np.empty((camera.image_height, camera.image_width, 3), np.uint8)
-        ptr = out.ctypes.data if isinstance(out, np.ndarray) else out.data_ptr()
         st = RtStats()
-        _check(self.L.rt_render(self.h, C.byref(camera), aa, ptr, C.byref(st)))
+        _check(self.L.rt_render(self.h, C.byref(camera), aa, _host_ptr(out), C.byref(st)))
         self.last_stats = st
         return out
 
-    def part_bytes(self, camera, rank, world):
-        return int(self.L.rt_part_bytes(C.byref(camera), rank, world))
+    def render_async(self, camera, aa, out):
+        """Enqueue a frame (rt_render_async); returns the ticket for wait()."""
+        t = C.c_int()
+        _check(self.L.rt_render_async(self.h, C.byref(camera), aa, _host_ptr(out), C.byref(t)))
+        return t.value
 
-    def render_part(self, camera, aa, rank, world, d_tiles_ptr, stream=0, want_stats=True):
-        """This GPU's interleaved tiles, packed, into DEVICE memory (e.g. a torch uint8 tensor's data_ptr())."""
+    def wait(self, ticket):
         st = RtStats()
-        _check(self.L.rt_render_part(self.h, C.byref(camera), aa, rank, world, d_tiles_ptr, stream,
+        _check(self.L.rt_wait(self.h, ticket, C.byref(st)))
+        self.last_stats = st
+        return st
+
+    def part_bytes(self, camera, aa, rank, world):
+        return int(self.L.rt_part_bytes(C.byref(camera), aa, rank, world))
+
+    def render_part(self, camera, aa, rank, world, d_rows_ptr, stream=0, want_stats=True):
+        """This GPU's interleaved row bands, packed, into DEVICE memory (e.g. a torch uint8 tensor's data_ptr())."""
+        st = RtStats()
+        _check(self.L.rt_render_part(self.h, C.byref(camera), aa, rank, world, d_rows_ptr, stream,
                                      C.byref(st) if want_stats else None))
         self.last_stats = st if want_stats else None
         return st
@@ -321,63 +348,91 @@ class RayTracer:
         self.last_stats = st if want_stats else None
         return st
 
-    def assemble(self, camera, world, d_parts_ptr, part_stride, d_frame_ptr, stream=0):
-        _check(self.L.rt_assemble_tiles(C.byref(camera), world, d_parts_ptr, part_stride, d_frame_ptr, stream))
+    def render_part_to_host(self, camera, aa, rank, world, host_frame_ptr):
+        """This GPU's bands rendered and copied straight into their rows of a host frame (rt_render_part_to_host)."""
+        st = RtStats()
+        _check(self.L.rt_render_part_to_host(self.h, C.byref(camera), aa, rank, world, host_frame_ptr, C.byref(st)))
+        self.last_stats = st
+        return st
+
+    def assemble(self, camera, aa, world, d_parts_ptr, part_stride, d_frame_ptr, stream=0):
+        _check(self.L.rt_assemble_parts(C.byref(camera), aa, world, d_parts_ptr, part_stride, d_frame_ptr, stream))
 
 
 # ----------------------------------------------------------------------------- multi-GPU plumbing (one process per GPU)
 #
-# The frame is cut into RT_TILE x RT_TILE pixel tiles numbered row-major; tile k belongs to rank k % world (the
-# reference deals rows round-robin to its threads the same way, raytracer.cpp:353).  Every rank renders its tiles
-# into a packed buffer [n_my_tiles][RT_TILE][RT_TILE][3]; rank 0 gathers the buffers (one collective per frame,
-# no other data-path communication) and scatters them into the row-major frame.
+# The frame is cut into bands of band_height(camera, aa, world) pixel rows; band b belongs to rank b % world (the
+# reference deals rows round-robin to its threads the same way, raytracer.cpp:353).  Every rank renders its bands
+# into a packed buffer [n_my_bands][band_h][width][3].  For a frame that has to end up on GPU 0, rank 0 gathers the
+# buffers (one collective per frame, no other data-path communication) and scatters them into the row-major
+# frame; for a frame that has to end up on the HOST, no gather is needed at all: every rank copies its own bands
+# over its own PCIe link into their rows of a shared page-locked frame (SharedHostFrame, rt_render_part_to_host).
 
 
-def tile_grid(width, height, world=1):
-    """Tile columns (incl. the phantom column that rt_b200.h describes) and tile rows."""
-    tx, ty = (width + RT_TILE - 1) // RT_TILE, (height + RT_TILE - 1) // RT_TILE
-    if world > 1 and tx % world == 0:
-        tx += 1
-    return tx, ty
+def band_height(camera, aa, world):
+    return int(cuda_lib().rt_band_height(C.byref(camera), aa, world))
 
 
-def part_tile_ids(width, height, rank, world):
-    tx, ty = tile_grid(width, height, world)
-    return range(rank, tx * ty, world)
+def part_band_ids(height, band_h, rank, world):
+    return range(rank, (height + band_h - 1) // band_h, world)
 
 
-def gather_parts(dist, my_tiles, all_parts, rank, dst=0):
-    """One gather of the packed tile buffers to `dst` (torch.distributed; NCCL on GPUs, gloo in the CPU tests).
+def gather_parts(dist, my_rows, all_parts, rank, dst=0):
+    """One gather of the packed band buffers to `dst` (torch.distributed; NCCL on GPUs, gloo in the CPU tests).
     all_parts is a [world, stride] tensor on dst, None elsewhere."""
-    dist.gather(my_tiles, list(all_parts.unbind(0)) if rank == dst else None, dst=dst)
+    dist.gather(my_rows, list(all_parts.unbind(0)) if rank == dst else None, dst=dst)
 
 
-def pack_tiles_host(frame, rank, world):
+def pack_bands_host(frame, band_h, rank, world):
     """Host restatement of the packed layout rt_render_part writes (tests and debugging only)."""
     h, w, _ = frame.shape
-    tx, _ = tile_grid(w, h, world)
-    ids = part_tile_ids(w, h, rank, world)
-    out = np.zeros((len(ids), RT_TILE, RT_TILE, 3), np.uint8)
-    for i, k in enumerate(ids):
-        y0, x0 = (k // tx) * RT_TILE, (k % tx) * RT_TILE
-        blk = frame[y0:y0 + RT_TILE, x0:x0 + RT_TILE]
-        out[i, :blk.shape[0], :blk.shape[1]] = blk
+    ids = part_band_ids(h, band_h, rank, world)
+    out = np.zeros((len(ids), band_h, w, 3), np.uint8)
+    for i, b in enumerate(ids):
+        blk = frame[b * band_h:(b + 1) * band_h]
+        out[i, :blk.shape[0]] = blk
     return out.reshape(-1)
 
 
-def assemble_tiles_host(parts, width, height, world):
-    """Host restatement of rt_assemble_tiles: parts is [world, stride] uint8."""
-    tx, _ = tile_grid(width, height, world)
+def assemble_bands_host(parts, width, height, band_h, world):
+    """Host restatement of rt_assemble_parts: parts is [world, stride] uint8."""
     frame = np.zeros((height, width, 3), np.uint8)
     for r in range(world):
-        ids = part_tile_ids(width, height, r, world)
-        tiles = np.asarray(parts[r][:len(ids) * RT_TILE * RT_TILE * 3]).reshape(len(ids), RT_TILE, RT_TILE, 3)
-        for i, k in enumerate(ids):
-            y0, x0 = (k // tx) * RT_TILE, (k % tx) * RT_TILE
-            hh, ww = min(RT_TILE, height - y0), min(RT_TILE, width - x0)
-            if ww > 0:
-                frame[y0:y0 + hh, x0:x0 + ww] = tiles[i, :hh, :ww]
+        ids = part_band_ids(height, band_h, r, world)
+        rows = np.asarray(parts[r][:len(ids) * band_h * width * 3]).reshape(len(ids), band_h, width, 3)
+        for i, b in enumerate(ids):
+            hh = min(band_h, height - b * band_h)
+            frame[b * band_h:b * band_h + hh] = rows[i, :hh]
     return frame
+
+
+class SharedHostFrame:
+    """A row-major RGB8 frame in POSIX shared memory, page-locked in every rank (rt_host_frame_*): each rank's
+    rt_render_part_to_host copies its bands straight into it, the frame is complete after a barrier."""
+
+    def __init__(self, dist, rank, nbytes, root=0):
+        self.L = cuda_lib()
+        self.rank, self.root, self.nbytes = rank, root, nbytes
+        self.ptr = C.c_void_p()
+        payload = [None]
+        if rank == root:
+            self.name = f"/rtb200_frame_{os.getpid()}"
+            _check(self.L.rt_host_frame_create(self.name.encode(), nbytes, C.byref(self.ptr)))
+            payload = [self.name]
+        if dist is not None:
+            dist.broadcast_object_list(payload, src=root)
+        self.name = payload[0]
+        if rank != root:
+            _check(self.L.rt_host_frame_open(self.name.encode(), nbytes, C.byref(self.ptr)))
+
+    def as_numpy(self):
+        buf = (C.c_ubyte * self.nbytes).from_address(self.ptr.value)
+        return np.frombuffer(buf, dtype=np.uint8)
+
+    def close(self):
+        if self.ptr:
+            self.L.rt_host_frame_close(self.ptr, self.nbytes, self.name.encode() if self.rank == self.root else None)
+            self.ptr = C.c_void_p()
 
 
 class PeerFrame:

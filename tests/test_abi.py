@@ -1,5 +1,5 @@
 """The C-ABI library: loads without a GPU, exports every symbol include/rt_b200.h declares, its host-only
-arithmetic (tile partition) is right, and it fails loudly — not silently on a CPU path — when no GPU is present."""
+arithmetic (row-band partition) is right, and it fails loudly — not silently on a CPU path — when no GPU is present."""
 import ctypes as C
 import os
 import re
@@ -21,23 +21,29 @@ def test_every_declared_symbol_is_exported():
     assert len(names) >= 15
     for n in names:
         assert hasattr(L, n), n
-    assert L.rt_abi_version() == 1
+    assert L.rt_abi_version() == 2
 
 
-def test_tile_partition_arithmetic():
+def test_band_partition_arithmetic():
+    """rt_band_height / rt_part_rows / rt_part_bytes: a pure function of (camera, aa, world); the parts' bands tile the
+    frame exactly once; the headline configuration deals single pixel rows like the reference (raytracer.cpp:353)."""
     L = H.rt_b200.cuda_lib()
     cam = H.RtCamera()
     for (w, h) in [(1, 1), (32, 32), (33, 31), (250, 190), (1440, 720), (7680, 3840)]:
         cam.image_width, cam.image_height = w, h
-        for world in (1, 2, 3, 4, 8):
-            tx, ty = H.rt_b200.tile_grid(w, h, world)  # includes the phantom column when tiles_x % world == 0
-            assert tx in ((w + 31) // 32, (w + 31) // 32 + 1) and (tx % world != 0 or world == 1)
-            tiles = tx * ty
-            per = [L.rt_part_tiles(C.byref(cam), r, world) for r in range(world)]
-            assert sum(per) == tiles
-            assert per == [len(range(r, tiles, world)) for r in range(world)]
-            assert all(L.rt_part_bytes(C.byref(cam), r, world) == per[r] * 32 * 32 * 3 for r in range(world))
-    assert L.rt_part_tiles(C.byref(cam), 2, 2) == -1  # rank out of range
+        for aa in (1, 2, 3, 4, 8, 16):
+            for world in (1, 2, 3, 4, 8):
+                bh = L.rt_band_height(C.byref(cam), aa, world)
+                assert bh >= 1 and (aa % 8 != 0 or bh == 1)
+                n_bands = (h + bh - 1) // bh
+                rows = [L.rt_part_rows(C.byref(cam), aa, r, world) for r in range(world)]
+                assert rows == [len(range(r, n_bands, world)) * bh for r in range(world)]
+                assert sum(rows) == n_bands * bh
+                assert all(L.rt_part_bytes(C.byref(cam), aa, r, world) == rows[r] * w * 3 for r in range(world))
+                assert list(H.rt_b200.part_band_ids(h, bh, 0, world)) == list(range(0, n_bands, world))
+    assert L.rt_part_rows(C.byref(cam), 1, 2, 2) == -1  # rank out of range
+    cam.image_width, cam.image_height = 7680, 3840
+    assert L.rt_band_height(C.byref(cam), 16, 8) == 1
 
 
 def test_no_cpu_fallback():
