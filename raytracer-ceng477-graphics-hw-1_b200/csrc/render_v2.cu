@@ -49,17 +49,20 @@ RT_DEV V3 clamp3(V3 c) {  // Vec3f::clamp(0, FLT_MAX), raytracer.cpp:451
     return mk(clamp_ref(c.x, 0.0f, FLT_MAX), clamp_ref(c.y, 0.0f, FLT_MAX), clamp_ref(c.z, 0.0f, FLT_MAX));
 }
 
-// per-lane path state
+// per-lane path state (scalars only: the compiler keeps a struct in registers only if nothing in it is indexed
+// dynamically, so the three stacks live in separate local arrays — see LaneStacks)
 struct Lane {
     int phase;
     int depth, npush, light, mat, hitprim;
     V3 color, Pt, n, dn;
     Ray ray;
     float limit;
+};
+struct LaneStacks {
     // reflection levels of the current path (folded back to front at the end of the path)
-    V3 local_stack[kMaxSupportedDepth + 1];
-    int mat_stack[kMaxSupportedDepth + 1];
-    int stack[kStackSize];
+    V3 *local_stack;  // [kMaxSupportedDepth + 1]
+    int *mat_stack;   // [kMaxSupportedDepth + 1]
+    int *stack;       // [kStackSize] traversal stack
 };
 
 RT_DEV void start_primary(const RenderParams &p, Lane &L, V3 E0, V3 Q, V3 U, V3 Vv, int sx, int sy) {
@@ -77,7 +80,7 @@ RT_DEV void start_primary(const RenderParams &p, Lane &L, V3 E0, V3 Q, V3 U, V3 
 // One ray per active lane through the BVH (closest-hit and any-hit share the loop), then the lane consumes its
 // result.  Returns true when the lane's path is finished; rgb then holds the quantised sample.
 template <bool FAR>
-RT_DEV bool trace_step(const RenderParams &p, Lane &L, V3 Ia, Counters &cnt, unsigned &r8, unsigned &g8, unsigned &b8) {
+RT_DEV bool trace_step(const RenderParams &p, Lane &L, const LaneStacks &S, V3 Ia, Counters &cnt, unsigned &r8, unsigned &g8, unsigned &b8) {
     const int phase = L.phase;
     const bool any = phase == kShadow;
     float tbest = L.limit;
@@ -102,7 +105,7 @@ RT_DEV bool trace_step(const RenderParams &p, Lane &L, V3 Ia, Counters &cnt, uns
                 }
             }
         } else {
-            int *sp = L.stack;  // pointer, not index: saves the index scaling on every push/pop
+            int *sp = S.stack;  // pointer, not index: saves the index scaling on every push/pop
             *sp++ = kSentinel;
             int node = 0;  // inner references are float4 indices (4 * node), leaves negative, see rt_internal.h
             const float4 *__restrict__ nodes = p.nodes;
@@ -242,8 +245,8 @@ RT_DEV bool trace_step(const RenderParams &p, Lane &L, V3 Ia, Counters &cnt, uns
         } else {
             const float4 m1 = __ldg(&p.materials[4 * (L.mat - 1) + 1]);
             if (__float_as_int(m1.w) != 0) {  // mirror: raytracer.cpp:430-439
-                L.local_stack[L.npush] = L.color;
-                L.mat_stack[L.npush] = L.mat;
+                S.local_stack[L.npush] = L.color;
+                S.mat_stack[L.npush] = L.mat;
                 L.npush++;
                 const V3 nn = L.hitprim < p.n_tris ? xyz(__ldg(&p.tri_nn[L.hitprim])) : normalize(L.n);
                 const float rc = dot(-L.dn, nn);
@@ -268,8 +271,8 @@ RT_DEV bool trace_step(const RenderParams &p, Lane &L, V3 Ia, Counters &cnt, uns
         int npush = L.npush;
         while (npush > 0) {  // fold the mirror levels back to front
             npush--;
-            const V3 km = xyz(__ldg(&p.materials[4 * (L.mat_stack[npush] - 1) + 3]));
-            result = clamp3(L.local_stack[npush] + mulv(result, km));
+            const V3 km = xyz(__ldg(&p.materials[4 * (S.mat_stack[npush] - 1) + 3]));
+            result = clamp3(S.local_stack[npush] + mulv(result, km));
         }
         r8 = quantise(result.x), g8 = quantise(result.y), b8 = quantise(result.z);
         L.phase = kIdle;
@@ -299,6 +302,10 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
     const V3 Ia = ld3(p.ambient);
     Counters cnt = {0u, 0u, 0u, 0u, 0u, 0u};
     Lane L;
+    V3 local_stack[kMaxSupportedDepth + 1];
+    int mat_stack[kMaxSupportedDepth + 1];
+    int stack[kStackSize];
+    const LaneStacks S = {local_stack, mat_stack, stack};
 
     for (;;) {
         unsigned item = 0;
@@ -333,7 +340,7 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
                         cnt.primary++;
                         do {
                             unsigned r8, g8, b8;
-                            if (trace_step<FAR>(p, L, Ia, cnt, r8, g8, b8)) sr += r8, sg += g8, sb += b8;
+                            if (trace_step<FAR>(p, L, S, Ia, cnt, r8, g8, b8)) sr += r8, sg += g8, sb += b8;
                         } while (__any_sync(0xffffffffu, L.phase != kIdle));
                     }
                 }
@@ -390,7 +397,7 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
                     continue;
                 }
                 unsigned r8, g8, b8;
-                if (trace_step<FAR>(p, L, Ia, cnt, r8, g8, b8)) {
+                if (trace_step<FAR>(p, L, S, Ia, cnt, r8, g8, b8)) {
                     if (f == 1) {
                         unsigned char *o = pixel_ptr(p, local_band, ly, px0 + lx, py0 + ly);
                         o[0] = (unsigned char) r8;

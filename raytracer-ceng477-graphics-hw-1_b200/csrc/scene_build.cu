@@ -575,6 +575,7 @@ int SceneBuild::run(const RtSceneDesc &d, int builder, int ploc_radius, float pl
             if (builder == RT_BUILD_AUTO || builder == RT_BUILD_SAH_GPU) {
                 DevTree &t = s.tree[builder == RT_BUILD_AUTO ? 1 : 0];
                 s.sah.n_nodes = t.n_used;  // the builder's node counter IS the tree's used-slot count
+                t.prim_order = s.sah.ids;  // ... and the index array it partitions IS the leaf order
                 enqueue_sah(s.bounds, np, s.sah, t, out.result, n_sms, stream);
                 n_candidates = builder == RT_BUILD_AUTO ? 2 : 1;
             }

@@ -314,6 +314,44 @@ def random_scene(seed, n_tris=40, n_spheres=4, n_lights=2, max_depth=3, width=96
                  [(cam, f"random_{seed}.ppm")])
 
 
+def tessellated_scene(name, levels):
+    """A shipped scene with every triangle cut into 4^levels coplanar sub-triangles (unshared vertices): the same
+    picture from ~10^6 primitives, full of exact-t ties on the new shared edges — the large-scene stress for the GPU
+    builders (multi-CTA PLOC, traversal stack depth) and for the tie ranks."""
+    base = golden_scene(name)
+    n = 1 << levels
+    v = base.vertices.astype(np.float64)
+    tri = base.triangles
+    a, b, c = v[tri[:, 0] - 1], v[tri[:, 1] - 1], v[tri[:, 2] - 1]
+    # barycentric lattice: point (i, j) = a + (b - a) i / n + (c - a) j / n, i + j <= n
+    ii, jj = np.meshgrid(np.arange(n + 1), np.arange(n + 1), indexing="ij")
+    keep = (ii + jj) <= n
+    li, lj = ii[keep], jj[keep]
+    index = -np.ones((n + 1, n + 1), np.int64)
+    index[li, lj] = np.arange(len(li))
+    pts = (a[:, None, :] + (b - a)[:, None, :] * (li / n)[None, :, None] + (c - a)[:, None, :] * (lj / n)[None, :, None]).astype(np.float32)
+    per = pts.shape[1]
+    small = []
+    for i in range(n):
+        for j in range(n - i):
+            small.append([index[i, j], index[i + 1, j], index[i, j + 1]])
+            if i + j + 1 < n:
+                small.append([index[i + 1, j], index[i + 1, j + 1], index[i, j + 1]])
+    small = np.array(small, np.int64)  # [4^levels, 3] lattice indices
+    nt = len(tri)
+    ids = (np.arange(nt)[:, None, None] * per + small[None, :, :] + 1).reshape(-1, 3)
+    mats = np.repeat(tri[:, 3], len(small))
+    new_tris = np.concatenate([ids, mats[:, None]], axis=1).astype(np.int32)
+    # spheres keep their centres: append the original vertices behind the lattice points
+    verts = np.concatenate([pts.reshape(-1, 3), base.vertices], axis=0)
+    off = nt * per
+    sph_ids = np.stack([base.spheres["material_id"], base.spheres["center_vertex_id"] + off], axis=1) if len(base.spheres) else np.zeros((0, 2), np.int32)
+    d = base.desc
+    return Scene(verts, new_tris, sph_ids, base.spheres["radius"] if len(base.spheres) else np.zeros(0, np.float32), base.materials["f"],
+                 base.materials["is_mirror"], base.lights, (d.ambient_light.x, d.ambient_light.y, d.ambient_light.z), d.shadow_ray_epsilon,
+                 list(d.background), d.max_recursion_depth, base.cameras)
+
+
 def scene_to_xml(sc, path):
     """Writes a Scene in the reference's XML grammar (floats with 9 significant digits round-trip through >>)."""
     d = sc.desc

@@ -483,3 +483,36 @@ def test_axis_parallel_rays(scene, cam_idx, w, h, aa):
     assert np.array_equal(want, got), H.diff_report(want, got)
     assert (st.primary_rays, st.reflection_rays, st.shadow_rays, st.shadow_occluded) == \
         (ost.primary_rays, ost.reflection_rays, ost.shadow_rays, ost.shadow_occluded)
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("builder", ["auto", "ploc", "sah_gpu", "lbvh"])
+def test_two_million_triangle_scene(builder):
+    """Beyond course-homework scale: horse_and_mug with every triangle cut into 64 coplanar pieces (2.02 M triangles,
+    1.4 M vertices, exact-t ties on every new edge).  PLOC runs as a cooperative multi-CTA kernel, the top-down builder
+    with thousands of CTAs per level; the tree must fit the traversal stack; the frame must equal the oracle's."""
+    B = H.rt_b200
+    sc = H.tessellated_scene("horse_and_mug", 3)
+    cam = sc.camera(0, 320, 160)
+    orc = H.OracleScene(sc)
+    want, ost = orc.render(cam, 1)
+    orc.close()
+    import time
+    t0 = time.perf_counter()
+    rt = H.RayTracer(sc, builder={"auto": B.RT_BUILD_AUTO, "ploc": B.RT_BUILD_PLOC_GPU, "sah_gpu": B.RT_BUILD_SAH_GPU, "lbvh": B.RT_BUILD_LBVH_GPU}[builder])
+    wall = time.perf_counter() - t0
+    inf = rt.info()
+    got = rt.render(cam, 1)
+    st = rt.last_stats
+    print(f"2M triangles, {builder}: kept builder {inf.builder}, {inf.bvh_nodes} nodes, depth {inf.bvh_max_depth}, SAH {inf.bvh_sah_cost:.1f} "
+          f"(ploc {inf.sah_cost_ploc:.1f} / sah {inf.sah_cost_sah:.1f}), build {inf.ms_build_device:.1f} ms device, {wall * 1e3:.0f} ms wall; "
+          f"render {st.ms_render:.2f} ms, replayed {st.replayed_closest}+{st.replayed_any} of {st.total_rays}")
+    assert inf.n_triangles == 2021248 and inf.bvh_max_depth <= 60
+    assert np.array_equal(want, got), H.diff_report(want, got)
+    assert (st.primary_rays, st.reflection_rays, st.shadow_rays, st.shadow_occluded) == \
+        (ost.primary_rays, ost.reflection_rays, ost.shadow_rays, ost.shadow_occluded)
+    # a larger frame for the timing line (no oracle: the CPU needs minutes for it)
+    big = sc.camera(0, 1440, 720)
+    rt.render(big, 1)
+    print(f"   1440x720: {rt.last_stats.ms_render:.2f} ms, {rt.last_stats.total_rays / rt.last_stats.ms_render / 1e3:.0f} Mrays/s")
+    rt.close()
