@@ -119,6 +119,27 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------- reference arm
 
 
+class quiet_stdout:
+    """The reference prints "Rendering ... with N cores..." from C (raytracer.cpp:368) on every render call: keep this
+    process's stdout to the one JSON line by pointing fd 1 at /dev/null for the duration."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(devnull, 1)
+        os.close(devnull)
+
+    def __exit__(self, *exc):
+        try:
+            import ctypes as C
+            C.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def workload_name(args):
     return f"{args.scene}.xml {args.width}x{args.height} output, {args.aa}x{args.aa} SSAA ({args.width * args.aa}x{args.height * args.aa} sub-samples)"
 
@@ -254,7 +275,8 @@ def small_configs(H, torch):
         rt.close()
         if H.ref_available():
             ref = H.RefScene(H.golden_scene_path(scene))
-            secs = min(ref.render(m["camera"], m["aa"])[1] for _ in range(3))
+            with quiet_stdout():
+                secs = min(ref.render(m["camera"], m["aa"])[1] for _ in range(3))
             rec.update(reference_render_s=secs, reference_build_s=ref.L.ref_build_seconds(ref.h), reference_mrays_s=st.total_rays / secs / 1e6,
                        e2e_speedup_vs_reference_render=secs * 1e3 / rec["e2e_ms"])
             ref.close()
@@ -465,18 +487,18 @@ def run_b200(args):
                                 "frac": frame_bytes / world / (kernel_ms * 1e-3) / 1e9 / hbm_peak},
                         "l1l2_cache": {"algorithmic_bytes_per_ray": CACHE_B_PER_RAY.get(args.scene),
                                        "achieved_gbs": kernel_rays_per_s * CACHE_B_PER_RAY.get(args.scene, 0) / 1e9}}
-        cfg = workload_config(args)
-        cfg.update({"rays_per_frame": rays, "primary": primary, "reflection": reflection,
-                    "shadow": shadow, "shadow_occluded": occluded, "parallelism": f"row_bands_h{H.rt_b200.band_height(cam, aa, world)}_interleaved_x{world}",
-                    "gather": "none" if world == 1 else ("fused: kernels store into rank 0's frame over NVLink P2P (CUDA IPC), one barrier" if peer is not None
-                                                        else "nccl gather of packed bands + scatter kernel"),
-                    "l2": "flushed between timed iterations (256 MiB write)", "bvh": {0: "default", 1: "lbvh_gpu", 2: "sah_host", 3: "ploc_gpu", 4: "auto", 5: "sah_gpu"}[info.builder],
-                    "bvh_nodes": info.bvh_nodes, "frame_sha256": frame_sha, "device_frame_sha256": device_sha})
+        details = {"rays_per_frame": rays, "primary": primary, "reflection": reflection,
+                   "shadow": shadow, "shadow_occluded": occluded, "parallelism": f"row_bands_h{H.rt_b200.band_height(cam, aa, world)}_interleaved_x{world}",
+                   "gather": "none" if world == 1 else ("fused: kernels store into rank 0's frame over NVLink P2P (CUDA IPC), one barrier" if peer is not None
+                                                       else "nccl gather of packed bands + scatter kernel"),
+                   "l2": "flushed between timed iterations (256 MiB write)", "bvh": {0: "default", 1: "lbvh_gpu", 2: "sah_host", 3: "ploc_gpu", 4: "auto", 5: "sah_gpu"}[info.builder],
+                   "bvh_nodes": info.bvh_nodes, "frame_sha256": frame_sha, "device_frame_sha256": device_sha}
         line = {"metric": "Mrays/s (primary + shadow + reflection)", "value": value, "unit": "Mrays/s", "n_gpus": world,
                 "steps": args.steps, "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "reference's shipped scene (tests/golden/scenes, deterministic; the metric is defined on it, not on synthetic data)",
-                "config": cfg,
+                "config": workload_config(args),  # the same object the reference arm prints
+                "frame": details,
                 "ms_per_frame": ms_per_step, "render_kernel_ms": kernel_ms, "wall_s_timed_region": wall_s,
                 "step_ms_rank0": [round(x, 3) for x in step_ms],
                 "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},

@@ -62,7 +62,6 @@ struct RtScene {
     void *arena = nullptr;
     SceneBuffers buf;
     RenderSlot slot[kFrameSlots];
-    unsigned next_ticket = 0;
     unsigned char *d_parts = nullptr;  // rt_render_multi / rt_render_part_to_host: this device's packed bands
     size_t parts_cap = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
@@ -824,9 +823,10 @@ int rt_render_async(RtScene *s, const RtCamera *cam, int aa, unsigned char *rgb_
     if (!rgb_out || !ticket) return fail(RT_ERR_INVALID, "rgb_out or ticket is NULL");
     DeviceGuard g;
     if (g.use(s->device) != 0) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
-    const int k = (int) (s->next_ticket % kFrameSlots);
+    int k = 0;  // the lowest free slot (a synchronous caller always reuses slot 0 and its buffers)
+    while (k < kFrameSlots && s->slot[k].busy) k++;
+    if (k == kFrameSlots) return fail(RT_ERR_STATE, "too many frames in flight on this handle (rt_wait the oldest first)");
     RenderSlot &sl = s->slot[k];
-    if (sl.busy) return fail(RT_ERR_STATE, "too many frames in flight on this handle (rt_wait the oldest first)");
     rc = slot_prepare(sl);
     if (rc != RT_OK) return rc;
     const size_t bytes = (size_t) cam->image_width * cam->image_height * 3;
@@ -852,15 +852,14 @@ int rt_render_async(RtScene *s, const RtCamera *cam, int aa, unsigned char *rgb_
     sl.dst = rgb_out;
     sl.bytes = bytes;
     sl.staged = !pinned_dst;
-    *ticket = (int) s->next_ticket;
-    s->next_ticket++;
+    *ticket = k;
     return RT_OK;
 }
 
 int rt_wait(RtScene *s, int ticket, RtStats *stats) {
     if (!s) return fail(RT_ERR_INVALID, "NULL scene");
-    RenderSlot &sl = s->slot[(unsigned) ticket % kFrameSlots];
-    if (!sl.busy) return fail(RT_ERR_STATE, "no frame in flight under this ticket");
+    if (ticket < 0 || ticket >= kFrameSlots || !s->slot[ticket].busy) return fail(RT_ERR_STATE, "no frame in flight under this ticket");
+    RenderSlot &sl = s->slot[ticket];
     DeviceGuard g;
     if (g.use(s->device) != 0) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
     sl.busy = false;

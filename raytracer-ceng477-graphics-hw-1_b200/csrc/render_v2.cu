@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
                 for (int by = 0; by < bpy; by++) {
                     for (int bx = 0; bx < bpx; bx++) {
                         start_primary(p, L, E0, Q, U, Vv, sx0 + bx * 8, sy0 + by * 4);
-                        cnt.primary++;
+                        cnt.primary += p.max_depth >= 0;  // a ray is a closest-hit query (raytracer.cpp:387: none when the depth limit is negative)
                         do {
                             unsigned r8, g8, b8;
                             if (trace_step<FAR>(p, L, S, Ia, cnt, r8, g8, b8)) sr += r8, sg += g8, sb += b8;
@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
                         ly = (b / nbx) * 4 + (l >> 3);
                         if (lx < sw && ly < sh) {
                             start_primary(p, L, E0, Q, U, Vv, px0 * f + lx, py0 * f + ly);
-                            cnt.primary++;
+                            cnt.primary += p.max_depth >= 0;
                         }
                     }
                 }
