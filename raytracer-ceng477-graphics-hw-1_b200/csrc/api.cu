@@ -204,9 +204,12 @@ ItemGeom item_geometry(const RtCamera *cam, int aa, int world) {
     ItemGeom g;
     const int nx = cam->image_width, ny = cam->image_height;
     if (aa % 8 == 0 && RT_ACC_REGS) {
+        // strips of one pixel row: 32 pixels wide (96 bytes = three whole sectors per store) when the frame has enough of
+        // them to give every resident warp ~100 items, narrower on smaller frames (a strip is f*f samples per pixel)
         g.acc_mode = 1;
         g.P = 32;
         g.Ph = 1;
+        while (g.P > 4 && (long long) ((nx + g.P - 1) / g.P) * ny / world < 96 * kNominalWarps) g.P /= 2;
     } else {
         g.acc_mode = 0;
         // P x P output pixels with P*f ~ 32 sub-samples a side (1024 sub-samples per item, P <= 16 when f > 1: the
