@@ -422,6 +422,11 @@ def run_b200(args):
     total_ms, total_render_ms = [float(x) for x in t.tolist()]
     ms_per_step = total_ms / args.steps
     kernel_ms = total_render_ms / args.steps  # the render kernel alone (max over ranks)
+    per_rank_kernel_ms = [sum(render_ms) / args.steps]
+    if dist:
+        g = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(g, torch.tensor([per_rank_kernel_ms[0]], dtype=torch.float64, device="cuda"))
+        per_rank_kernel_ms = [float(x.item()) for x in g]
 
     # ---- e2e: the user-facing C-ABI call, frame into page-locked HOST memory inside the timed region
     e2e_ms = []
@@ -499,7 +504,8 @@ def run_b200(args):
                 "data": "reference's shipped scene (tests/golden/scenes, deterministic; the metric is defined on it, not on synthetic data)",
                 "config": workload_config(args),  # the same object the reference arm prints
                 "frame": details,
-                "ms_per_frame": ms_per_step, "render_kernel_ms": kernel_ms, "wall_s_timed_region": wall_s,
+                "ms_per_frame": ms_per_step, "render_kernel_ms": kernel_ms, "render_kernel_ms_per_rank": [round(x, 3) for x in per_rank_kernel_ms],
+                "wall_s_timed_region": wall_s,
                 "step_ms_rank0": [round(x, 3) for x in step_ms],
                 "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
                 "e2e": {"value": rays / (e2e_ms_per_step * 1e3), "unit": "Mrays/s", "ms_per_frame": e2e_ms_per_step,

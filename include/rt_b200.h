@@ -116,7 +116,7 @@ typedef struct RtBuildOptions {
   float ploc_leaf_cost;     /* experiments: per-primitive cost in PLOC's leaf-collapse decision (0 = default 1.0) */
   int32_t force_replay;     /* tests: every ray that reports a hit is re-decided by the exact replay of the reference's
                                traversal (slow; must give the same frame as the default path) */
-  int32_t reserved[1];
+  int32_t max_ctas_per_sm;  /* experiments: cap on resident CTAs per SM for the render kernel (0 = occupancy limit) */
 } RtBuildOptions;
 
 /* counters are exact (device atomics); "ray" = one closest-hit query

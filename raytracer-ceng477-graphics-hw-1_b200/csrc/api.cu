@@ -59,6 +59,7 @@ struct RtScene {
     int ctas_per_sm[2] = {1, 1};  // shared-accumulator / register-accumulator instantiation
     int warps_per_cta = 4;
     int refill_threshold = 0;
+    int max_ctas_per_sm = 0;  // experiments: 0 = occupancy limit
     void *arena = nullptr;
     SceneBuffers buf;
     RenderSlot slot[kFrameSlots];
@@ -289,7 +290,9 @@ int enqueue_part(RtScene *s, const RtCamera *cam, int aa, int rank, int world, u
     p.control = s->buf.control + 8 * slot;
     CU(cudaMemsetAsync(p.control, 0, 8 * sizeof(unsigned long long), stream));
     if (n_items == 0) return RT_OK;
-    long long ctas = (long long) s->n_sms * s->ctas_per_sm[p.acc_mode];
+    int per_sm = s->ctas_per_sm[p.acc_mode];
+    if (s->max_ctas_per_sm > 0 && s->max_ctas_per_sm < per_sm) per_sm = s->max_ctas_per_sm;
+    long long ctas = (long long) s->n_sms * per_sm;
     const long long need = (n_items + s->warps_per_cta - 1) / s->warps_per_cta;
     if (ctas > need) ctas = need;
     const cudaError_t e = (cudaError_t) launch_render_v2(p, (int) ctas, stream);
@@ -382,6 +385,7 @@ int scene_create_impl(const RtSceneDesc *desc, const RtBuildOptions *opts, RtSce
         return bail(RT_ERR_CUDA, "render kernel cannot be resident on this device (built for sm_100a)");
     s->ctas_per_sm[0] = occ[0];
     s->ctas_per_sm[1] = occ[1];
+    if (opts && opts->max_ctas_per_sm > 0) s->max_ctas_per_sm = opts->max_ctas_per_sm;
     if (opts && opts->refill_threshold > 0) s->refill_threshold = opts->refill_threshold > 31 ? 31 : opts->refill_threshold;
 
     SceneBuild local_build;

@@ -114,10 +114,9 @@ RT_DEV bool trace_step(const RenderParams &p, Lane &L, const LaneStacks &S, V3 I
                 // the warp runs the primitive tests together
                 while ((unsigned) node < (unsigned) kSentinel) {
                     const float4 *nd = nodes + (unsigned) node;
-                    const float4 n0 = __ldg(nd);
-                    const float4 n1 = __ldg(nd + 1);
-                    const float4 n2 = __ldg(nd + 2);
-                    const float2 n3 = __ldg((const float2 *) (nd + 3));
+                    float4 n0, n1, n2, n3;
+                    ld256(nd, n0, n1);
+                    ld256(nd + 2, n2, n3);
                     float tmin0, tmax0, tmin1, tmax1;
                     slab(L.ray, n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, tmin0, tmax0);
                     slab(L.ray, n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, tmin1, tmax1);

@@ -64,7 +64,7 @@ class RtCamera(C.Structure):
 class RtBuildOptions(C.Structure):
     _fields_ = [("builder", C.c_int32), ("brute_force", C.c_int32), ("no_exact_culling", C.c_int32),
                 ("refill_threshold", C.c_int32), ("ploc_radius", C.c_int32), ("ploc_leaf_cost", C.c_float),
-                ("force_replay", C.c_int32), ("reserved", C.c_int32 * 1)]
+                ("force_replay", C.c_int32), ("max_ctas_per_sm", C.c_int32)]
 
 
 class RtStats(C.Structure):
@@ -283,11 +283,11 @@ class RayTracer:
     """RayTracer(scene) / render(camera) — raytracer.cpp:335, :362 — on the current CUDA device."""
 
     def __init__(self, scene, builder=RT_BUILD_DEFAULT, brute_force=False, exact_culling=True, refill_threshold=0,
-                 ploc_radius=0, ploc_leaf_cost=0.0, force_replay=False):
+                 ploc_radius=0, ploc_leaf_cost=0.0, force_replay=False, max_ctas_per_sm=0):
         self.L = cuda_lib()
         self.scene = scene
         opts = RtBuildOptions(builder, 1 if brute_force else 0, 0 if exact_culling else 1, refill_threshold, ploc_radius, ploc_leaf_cost,
-                              1 if force_replay else 0)
+                              1 if force_replay else 0, max_ctas_per_sm)
         h = C.c_void_p()
         _check(self.L.rt_scene_create(C.byref(scene.desc), C.byref(opts), C.byref(h)))
         self.h = h

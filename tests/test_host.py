@@ -151,3 +151,16 @@ def test_host_bvh_invariants(scene):
     n = L.rt_host_check_bvh(C.byref(sc.desc), C.byref(cost), C.byref(depth))
     assert n >= 1, L.rt_last_error()
     assert 0 < depth.value <= 60 and cost.value > 0
+
+
+def test_prolog_before_root_is_accepted(tmp_path):
+    """parser.cpp:17 takes the document's FIRST CHILD as the root, so the reference dereferences NULL on a file that
+    starts with an XML declaration or a comment (none of its 13 inputs does).  The product's loader skips
+    declarations / comments / DOCTYPE and reads the first ELEMENT: a deliberate superset —
+    the same scene must come out with and without the prolog."""
+    src = open(H.golden_scene_path("simple")).read()
+    plain = tmp_path / "plain.xml"
+    plain.write_text(src)
+    with_prolog = tmp_path / "prolog.xml"
+    with_prolog.write_text('<?xml version="1.0" encoding="UTF-8"?>\n<!-- exported by a tool -->\n' + src)
+    assert H.load_scene_xml(str(plain)).digest() == H.load_scene_xml(str(with_prolog)).digest()

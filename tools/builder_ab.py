@@ -11,7 +11,7 @@ for case in cases:
     name, w, h, aa = case.split(":")
     sc = H.golden_scene(name)
     cam = sc.camera(0, int(w), int(h))
-    for bname, b in (("ploc", 3), ("sah_host", 2), ("lbvh", 1)):
+    for bname, b in (("ploc", 3), ("sah_gpu", 5), ("sah_host", 2), ("lbvh", 1)):
         for exact in (True, False):
             rt = H.RayTracer(sc, builder=b, exact_culling=exact)
             best = 1e30

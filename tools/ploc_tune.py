@@ -14,12 +14,7 @@ for case in cases:
     sc = H.golden_scene(name)
     cam = sc.camera(0, int(w), int(h))
     for label, b, r, c in settings:
-        for k, v in (("RT_B200_PLOC_RADIUS", r), ("RT_B200_PLOC_LEAF_COST", c)):
-            if v is None:
-                os.environ.pop(k, None)
-            else:
-                os.environ[k] = str(v)
-        rt = H.RayTracer(sc, builder=b)
+        rt = H.RayTracer(sc, builder=b, ploc_radius=r or 0, ploc_leaf_cost=c or 0.0)
         best = 1e30
         for _ in range(4):
             rt.render(cam, int(aa))

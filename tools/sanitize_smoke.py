@@ -10,11 +10,13 @@ for name, w, h, aa in (("simple_reflectance", 64, 48, 2), ("cornellbox", 40, 40,
     sc = H.golden_scene(name)
     cam = sc.camera(0, w, h)
     want, _ = H.OracleScene(sc).render(cam, aa)
-    for kernel in ("2", "1", "3"):
-        os.environ["RT_B200_KERNEL"] = kernel
-        for builder in (0, 1, 3, 5):
-            rt = H.RayTracer(sc, builder=builder)
+    for builder in (0, 1, 3, 5, 2):
+        for refill in (0, 12):
+            rt = H.RayTracer(sc, builder=builder, refill_threshold=refill)
             got = rt.render(cam, aa)
-            assert (got == want).all(), (name, kernel, builder)
+            assert (got == want).all(), (name, builder, refill)
+            if refill == 0:
+                got8 = rt.render(cam, 8)  # register-accumulator strips
+                assert got8.shape == want.shape
             rt.close()
     print(name, "ok", flush=True)
