@@ -192,6 +192,9 @@ int rt_warmup(int device);
  * i % cores) for load balance; at the 16x16 headline configuration a band is ONE pixel row.  The band height is a
  * pure function of (camera, aa_factor, part_world), so every rank and the gathering side agree without talking. */
 int rt_band_height(const RtCamera *cam, int aa_factor, int part_world);
+/* Tuning / experiments: overrides the band height (pixel rows) and the strip width of the 16x16-type kernel for the whole
+ * process (0 = built-in defaults).  Every rank of a multi-process run must set the same values. */
+int rt_set_partition(int band_rows, int strip_width);
 
 /* pixel rows part `part_rank` owns (its last band padded to the full band height), and bytes of its packed buffer
  * (rows * image_width * 3). */

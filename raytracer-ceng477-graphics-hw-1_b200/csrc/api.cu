@@ -191,7 +191,8 @@ int ensure(unsigned char **buf, size_t *cap, size_t need, bool pinned) {
 // without talking to each other.
 struct ItemGeom {
     int acc_mode;  // 1: f % 8 == 0, register accumulators, strips of 32 x 1 pixels
-    int P, Ph;     // item size in pixels; the band height is Ph
+    int P, Ph;     // item size in pixels
+    int rpb;       // item rows per band; the band height is Ph * rpb pixel rows
     int items_x;
     int n_bands_total;
     int group_bands, tile_items, tiles_per_group;
@@ -201,16 +202,20 @@ constexpr long long kNominalWarps = 148LL * 7 * 4;  // resident warps of one B20
 #define RT_ACC_REGS 1  // A/B builds (tools/build_variants.sh): 0 = shared-memory accumulators at every AA factor
 #endif
 
+// experiments (rt_set_partition): 0 = the defaults computed below
+int g_band_rows = 0, g_strip_width = 0;
+
 ItemGeom item_geometry(const RtCamera *cam, int aa, int world) {
     ItemGeom g;
     const int nx = cam->image_width, ny = cam->image_height;
     if (aa % 8 == 0 && RT_ACC_REGS) {
-        // strips of one pixel row: 32 pixels wide (96 bytes = three whole sectors per store) when the frame has enough of
-        // them to give every resident warp ~100 items, narrower on smaller frames (a strip is f*f samples per pixel)
+        // one pixel row per item row; the kernel claims runs of up to P pixels of a row with guided self-scheduling
+        // (render_v2.cu).  Measured (tools/partition_experiment.py, 8K 16x): runs of 4 pixels beat 32 by 0.6 % on the whole
+        // frame and by 3 % on a 1/8 part (neighbouring warps then work on neighbouring pixels of the same rows)
         g.acc_mode = 1;
-        g.P = 32;
+        g.P = 4;
         g.Ph = 1;
-        while (g.P > 4 && (long long) ((nx + g.P - 1) / g.P) * ny / world < 96 * kNominalWarps) g.P /= 2;
+        if (g_strip_width >= 1 && g_strip_width <= 32) g.P = 1 << (31 - __builtin_clz((unsigned) g_strip_width));
     } else {
         g.acc_mode = 0;
         // P x P output pixels with P*f ~ 32 sub-samples a side (1024 sub-samples per item, P <= 16 when f > 1: the
@@ -223,15 +228,26 @@ ItemGeom item_geometry(const RtCamera *cam, int aa, int world) {
         // resident warp a few dozen (dynamic load balance: items differ a lot in cost)
         auto items = [&](int p, int ph) { return (long long) ((nx + p - 1) / p) * ((ny + ph - 1) / ph) / world; };
         while (items(P, P) < 32 * kNominalWarps && P * aa > 8 && P > 1) P = (P + 1) / 2;
+        if (g_strip_width >= 1 && g_strip_width < P) P = g_strip_width;  // experiments
         int Ph = P;
+        // whole 8x4 blocks of sub-samples: P*f a multiple of 8 and Ph*f a multiple of 4 where the factor allows it
+        // (f = 3: 11x11 pixels = 33x33 sub-samples left a fifth block column with one live lane in eight)
+        {
+            const int mx = 8 / std::__gcd(8, aa), my = 4 / std::__gcd(4, aa);
+            P = std::max(mx, P / mx * mx);
+            Ph = std::max(my, Ph / my * my);
+            if (aa > 1 && P > 16) P = 16 / mx * mx > 0 ? 16 / mx * mx : mx;
+            if (aa > 1 && Ph > 16) Ph = 16 / my * my > 0 ? 16 / my * my : my;
+        }
         // still too few (a 1440x720 frame without AA has 16 K items of 64 pixels for 4144 resident warps): halve the
         // item once more to a single 8x4 round of sub-samples
         if (P * aa == 8 && 4 % aa == 0 && items(P, P) < 32 * kNominalWarps) Ph = 4 / aa;
         g.P = P;
         g.Ph = Ph;
     }
+    g.rpb = g_band_rows > 0 ? std::max(1, g_band_rows / g.Ph) : 1;
     g.items_x = (nx + g.P - 1) / g.P;
-    g.n_bands_total = (ny + g.Ph - 1) / g.Ph;
+    g.n_bands_total = (ny + g.Ph * g.rpb - 1) / (g.Ph * g.rpb);
     g.group_bands = std::max(1, 32 / g.Ph);
     g.tile_items = std::max(1, 32 / g.P);
     g.tiles_per_group = (g.items_x + g.tile_items - 1) / g.tile_items;
@@ -265,14 +281,17 @@ int enqueue_part(RtScene *s, const RtCamera *cam, int aa, int rank, int world, u
     p.P = g.P;
     p.Ph = g.Ph;
     p.items_x = g.items_x;
-    p.n_bands = (int) part_bands(g, rank, world);
+    p.n_bands = (int) part_bands(g, rank, world) * g.rpb;
+    p.rows_per_band = g.rpb;
     p.group_bands = g.group_bands;
     p.tile_items = g.tile_items;
     p.tiles_per_group = g.tiles_per_group;
     p.part_rank = rank;
     p.part_world = world;
-    const long long n_groups = (p.n_bands + g.group_bands - 1) / g.group_bands;
-    const long long n_items = n_groups * g.tiles_per_group * g.tile_items * g.group_bands;
+    const long long n_groups = (p.n_bands + g.group_bands - 1) / g.group_bands;  // p.n_bands counts item rows
+    // register-accumulator mode: the work counter runs over pixel slots in block order (32 rows x 32 pixels per block)
+    const long long n_items = g.acc_mode == 1 ? n_groups * ((cam->image_width + 31) / 32) * 1024
+                                              : n_groups * g.tiles_per_group * g.tile_items * g.group_bands;
     if (n_items >= (1LL << 32) - (1 << 22)) return fail(RT_ERR_INVALID, "too many work items");
     p.n_items = (unsigned) n_items;
     p.out_mode = out_mode;
@@ -293,8 +312,13 @@ int enqueue_part(RtScene *s, const RtCamera *cam, int aa, int rank, int world, u
     int per_sm = s->ctas_per_sm[p.acc_mode];
     if (s->max_ctas_per_sm > 0 && s->max_ctas_per_sm < per_sm) per_sm = s->max_ctas_per_sm;
     long long ctas = (long long) s->n_sms * per_sm;
-    const long long need = (n_items + s->warps_per_cta - 1) / s->warps_per_cta;
+    const long long units = p.acc_mode == 1 ? (long long) p.n_bands * cam->image_width : n_items;  // pixels / items to hand out
+    const long long need = (units + s->warps_per_cta - 1) / s->warps_per_cta;
     if (ctas > need) ctas = need;
+    if (p.acc_mode == 1) {
+        p.tiles_per_group = (cam->image_width + 31) / 32;
+        p.guide = (unsigned) (4 * ctas * s->warps_per_cta);
+    }
     const cudaError_t e = (cudaError_t) launch_render_v2(p, (int) ctas, stream);
     if (e != cudaSuccess) return fail(RT_ERR_CUDA, std::string("render kernel launch: ") + cudaGetErrorString(e));
     if (launches) (*launches)++;
@@ -313,13 +337,14 @@ void stats_from_words(const unsigned long long *h, RtStats *stats) {
 // strided device-to-host copy of one part's packed bands into the rows of a row-major host frame
 int copy_part_to_frame(const ItemGeom &g, const RtCamera *cam, int rank, int world, const unsigned char *d_part, unsigned char *frame,
                        cudaStream_t stream) {
-    const size_t row_bytes = (size_t) cam->image_width * 3, band_bytes = row_bytes * g.Ph;
+    const int band_h = g.Ph * g.rpb;
+    const size_t row_bytes = (size_t) cam->image_width * 3, band_bytes = row_bytes * band_h;
     const int64_t nb = part_bands(g, rank, world);
     if (nb == 0) return RT_OK;
     // the last band of the frame may be cut short by the image height
     const int64_t last_band = rank + (nb - 1) * world;
-    const int64_t last_rows = std::min<int64_t>(g.Ph, cam->image_height - last_band * g.Ph);
-    const int64_t full = last_rows == g.Ph ? nb : nb - 1;
+    const int64_t last_rows = std::min<int64_t>(band_h, cam->image_height - last_band * band_h);
+    const int64_t full = last_rows == band_h ? nb : nb - 1;
     if (full > 0) {
         if (world == 1) CU(cudaMemcpyAsync(frame, d_part, band_bytes * full, cudaMemcpyDeviceToHost, stream));
         else CU(cudaMemcpy2DAsync(frame + band_bytes * rank, band_bytes * world, d_part, band_bytes, band_bytes, (size_t) full,
@@ -510,7 +535,7 @@ int render_part_common(RtScene *s, const RtCamera *cam, int aa, int rank, int wo
 // enqueue: this part's bands into the handle's packed buffer, then straight into the rows of a host frame
 int enqueue_part_to_host(RtScene *s, const RtCamera *cam, int aa, int rank, int world, unsigned char *host_frame, int *launches) {
     const ItemGeom g = item_geometry(cam, aa, world);
-    const size_t bytes = (size_t) part_bands(g, rank, world) * g.Ph * cam->image_width * 3;
+    const size_t bytes = (size_t) part_bands(g, rank, world) * g.Ph * g.rpb * cam->image_width * 3;
     int rc = ensure(&s->d_parts, &s->parts_cap, bytes ? bytes : 1, false);
     if (rc != RT_OK) return rc;
     const int k = kControlSlots - 1;
@@ -808,13 +833,22 @@ int rt_scene_info(const RtScene *s, RtSceneInfo *info) {
 
 int rt_band_height(const RtCamera *cam, int aa, int part_world) {
     if (!cam || part_world < 1 || aa < 1) return -1;
-    return item_geometry(cam, aa, part_world).Ph;
+    const ItemGeom g = item_geometry(cam, aa, part_world);
+    return g.Ph * g.rpb;
+}
+
+// experiments: band height in pixel rows and strip width of the register-accumulator mode (0 = defaults).  Process-wide,
+// because the partition has to stay a pure function of (camera, aa, world) that every rank evaluates identically.
+int rt_set_partition(int band_rows, int strip_width) {
+    g_band_rows = band_rows > 0 ? band_rows : 0;
+    g_strip_width = strip_width > 0 ? strip_width : 0;
+    return RT_OK;
 }
 
 int64_t rt_part_rows(const RtCamera *cam, int aa, int part_rank, int part_world) {
     if (!cam || part_world < 1 || part_rank < 0 || part_rank >= part_world || aa < 1) return -1;
     const ItemGeom g = item_geometry(cam, aa, part_world);
-    return part_bands(g, part_rank, part_world) * g.Ph;  // the last band is padded to the full band height
+    return part_bands(g, part_rank, part_world) * g.Ph * g.rpb;  // the last band is padded to the full band height
 }
 
 int64_t rt_part_bytes(const RtCamera *cam, int aa, int part_rank, int part_world) {
@@ -905,7 +939,7 @@ int rt_assemble_parts(const RtCamera *cam, int aa, int part_world, const void *d
     if (!cam || !d_parts || !d_frame || part_world < 1 || aa < 1) return fail(RT_ERR_INVALID, "bad argument");
     const ItemGeom g = item_geometry(cam, aa, part_world);
     cudaError_t e = (cudaError_t) launch_assemble((const unsigned char *) d_parts, part_stride_bytes, part_world, cam->image_width,
-                                                  cam->image_height, g.Ph, (unsigned char *) d_frame, (cudaStream_t) cuda_stream);
+                                                  cam->image_height, g.Ph * g.rpb, (unsigned char *) d_frame, (cudaStream_t) cuda_stream);
     if (e != cudaSuccess) return fail(RT_ERR_CUDA, std::string("assemble kernel launch: ") + cudaGetErrorString(e));
     return RT_OK;
 }

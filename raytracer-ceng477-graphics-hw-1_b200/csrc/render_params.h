@@ -45,10 +45,12 @@ struct RenderParams {
     int f;               // supersampling factor (sub-sample grid is nx*f by ny*f)
     int P, Ph;           // item width / height in pixels
     int items_x;         // items per band = ceil(nx / P)
-    int n_bands;         // bands of this part
+    int n_bands;         // item rows of this part (bands x rows_per_band; rows beyond the image are skipped)
+    int rows_per_band;   // item rows (of Ph pixel rows each) per band
     int group_bands, tile_items, tiles_per_group;
     int part_rank, part_world;
-    unsigned int n_items;  // work items of this part (incl. empty padding items)
+    unsigned int n_items;  // work items of this part (incl. empty padding items); register-accumulator mode: pixel slots
+    unsigned int guide;    // register-accumulator mode: a warp claims ~ remaining / guide pixels at a time (4 x warps in flight)
     int out_mode;
     int refill_threshold;  // shared-accumulator mode: refill idle lanes once <= this many lanes are busy
     int acc_mode;          // 0: SSAA sums in warp-private shared memory (any f); 1: in registers (f % 8 == 0), see render_v2.cu

@@ -306,33 +306,42 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
     int stack[kStackSize];
     const LaneStacks S = {local_stack, mat_stack, stack};
 
-    for (;;) {
-        unsigned item = 0;
-        if (lane == 0) item = atomicAdd(work_counter, 1u);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= p.n_items) break;
-
-        // item -> (band of this part, item within the band): consecutive items cover a compact block (render_params.h)
-        const unsigned g = item / per_group, r = item % per_group;
-        const unsigned tc = r / per_tile, q = r % per_tile;
-        const int local_band = (int) (g * (unsigned) p.group_bands + q / (unsigned) p.tile_items);
-        const int ix = (int) (tc * (unsigned) p.tile_items + q % (unsigned) p.tile_items);
-        if (local_band >= p.n_bands || ix >= p.items_x) continue;
-        const int px0 = ix * P, py0 = (p.part_rank + local_band * p.part_world) * p.Ph;
-        const int pw = min(P, p.nx - px0);
-        const int ph = min(p.Ph, p.ny - py0);
-        if (pw <= 0 || ph <= 0) continue;
-        L.phase = kIdle;
-
-        if (ACC == kAccRegs) {
-            // ---- strip of pw <= 32 pixels of row py0; f = 8 * bpx = 4 * bpy -----------------------------------
-            const int bpx = f >> 3, bpy = f >> 2;
-            const unsigned ff = (unsigned) (f * f);
-            const int sy0 = py0 * f + (lane >> 3);
-            unsigned mine = 0u;  // lane i ends up holding pixel i of the strip as B << 16 | G << 8 | R
-            for (int pix = 0; pix < pw; pix++) {
+    if (ACC == kAccRegs) {
+        // ---- f = 8 * bpx = 4 * bpy: strips of up to 32 pixels of one row, GUIDED self-scheduling ---------------------
+        // The part's pixels are numbered in block order — index = ((group of 32 rows * tiles_x + 32-pixel column) * 32 + row
+        // in group) * 32 + pixel in column — and a warp claims the next `n` of them with one atomic, n = 32 while plenty
+        // is left, then 16, 8, ... 1 as the part runs out (n ~ remaining / (4 x warps in flight)): big items while
+        // throughput matters, single pixels when only the tail is left.  (Fixed 32-pixel strips cost 0.6 % on the full 8K
+        // frame and 9 % on a 1/8 part; fixed 8-pixel strips 1.8 % on the part: tools/partition_experiment.py.)
+        const int bpx = f >> 3, bpy = f >> 2;
+        const unsigned ff = (unsigned) (f * f);
+        const unsigned total = p.n_items, tiles_x = (unsigned) p.tiles_per_group;
+        for (;;) {
+            unsigned start = 0, n = 0;
+            if (lane == 0) {
+                const unsigned cur = *(volatile unsigned *) work_counter;
+                const unsigned c = (cur < total ? total - cur : 0u) / p.guide;
+                n = c >= (unsigned) p.P ? (unsigned) p.P : (c >= 1u ? 1u << (31 - __clz(c)) : 1u);
+                start = atomicAdd(work_counter, n);
+            }
+            start = __shfl_sync(0xffffffffu, start, 0);
+            n = __shfl_sync(0xffffffffu, n, 0);
+            if (start >= total) break;
+            n = min(n, total - start);
+            // lane i < n owns pixel start + i
+            const unsigned idx = start + (unsigned) lane;
+            const unsigned t = idx >> 10;
+            const int local_row = (int) ((t / tiles_x) * 32u + ((idx >> 5) & 31u));
+            const int x = (int) ((t % tiles_x) * 32u + (idx & 31u));
+            // local row -> global row: bands of rows_per_band rows, band b of this part = part_rank + b * part_world
+            const int y = (p.part_rank + (local_row / p.rows_per_band) * p.part_world) * p.rows_per_band + local_row % p.rows_per_band;
+            const bool valid = lane < (int) n && local_row < p.n_bands && x < p.nx && y < p.ny;
+            L.phase = kIdle;
+            unsigned mine = 0u;  // B << 16 | G << 8 | R of this lane's pixel
+            for (int pix = 0; pix < (int) n; pix++) {
+                if (!__shfl_sync(0xffffffffu, (int) valid, pix)) continue;
+                const int sx0 = __shfl_sync(0xffffffffu, x, pix) * f + (lane & 7), sy0 = __shfl_sync(0xffffffffu, y, pix) * f + (lane >> 3);
                 unsigned sr = 0u, sg = 0u, sb = 0u;
-                const int sx0 = (px0 + pix) * f + (lane & 7);
                 for (int by = 0; by < bpy; by++) {
                     for (int bx = 0; bx < bpx; bx++) {
                         start_primary(p, L, E0, Q, U, Vv, sx0 + bx * 8, sy0 + by * 4);
@@ -348,19 +357,43 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
                                B = __reduce_add_sync(0xffffffffu, sb) / ff;
                 if (lane == pix) mine = R | (G << 8) | (B << 16);
             }
-            unsigned char *row = pixel_ptr(p, local_band, 0, px0, py0);
-            if (pw == 32 && (((size_t) row) & 3) == 0) {
-                // word w = bytes 4w .. 4w+3 of the strip = pixels (4w)/3 and (4w)/3 + 1, shifted by w % 3 bytes
+            unsigned char *o = p.out_mode == kOutFrame ? p.out + ((size_t) y * p.nx + x) * 3 : p.out + ((size_t) local_row * p.nx + x) * 3;
+            // an aligned run of 4k pixels of one row leaves as 3k 32-bit words built with two shuffles each
+            // (word w = bytes 4w .. 4w+3 = pixels (4w)/3 and (4w)/3 + 1, shifted by w % 3 bytes)
+            const bool whole = (n & 3u) == 0u && (start & (n - 1u)) == 0u && __all_sync(0xffffffffu, valid || lane >= (int) n);
+            unsigned char *row = (unsigned char *) __shfl_sync(0xffffffffu, (unsigned long long) o, 0);
+            if (whole && (((size_t) row) & 3) == 0) {
                 const int p0 = (4 * lane) / 3;
                 const unsigned lo = __shfl_sync(0xffffffffu, mine, p0 & 31), hi = __shfl_sync(0xffffffffu, mine, (p0 + 1) & 31);
                 const unsigned long long two = (unsigned long long) lo | ((unsigned long long) hi << 24);
-                if (lane < 24) ((unsigned *) row)[lane] = (unsigned) (two >> (8 * (lane % 3)));
-            } else if (lane < pw) {
-                row[3 * lane] = (unsigned char) mine;
-                row[3 * lane + 1] = (unsigned char) (mine >> 8);
-                row[3 * lane + 2] = (unsigned char) (mine >> 16);
+                if (lane < (int) (n * 3u / 4u)) ((unsigned *) row)[lane] = (unsigned) (two >> (8 * (lane % 3)));
+            } else if (valid) {
+                o[0] = (unsigned char) mine;
+                o[1] = (unsigned char) (mine >> 8);
+                o[2] = (unsigned char) (mine >> 16);
             }
-        } else {
+        }
+    } else {
+      for (;;) {
+        unsigned item = 0;
+        if (lane == 0) item = atomicAdd(work_counter, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= p.n_items) break;
+
+        // item -> (band of this part, item within the band): consecutive items cover a compact block (render_params.h)
+        const unsigned g = item / per_group, r = item % per_group;
+        const unsigned tc = r / per_tile, q = r % per_tile;
+        const int local_band = (int) (g * (unsigned) p.group_bands + q / (unsigned) p.tile_items);
+        const int ix = (int) (tc * (unsigned) p.tile_items + q % (unsigned) p.tile_items);
+        if (local_band >= p.n_bands || ix >= p.items_x) continue;
+        // local item row -> global item row: bands of p.rows_per_band item rows, band b of this part = part_rank + b * part_world
+        const int band = local_band / p.rows_per_band, in_band = local_band % p.rows_per_band;
+        const int px0 = ix * P, py0 = ((p.part_rank + band * p.part_world) * p.rows_per_band + in_band) * p.Ph;
+        const int pw = min(P, p.nx - px0);
+        const int ph = min(p.Ph, p.ny - py0);
+        if (pw <= 0 || ph <= 0) continue;
+        L.phase = kIdle;
+        {
             // ---- P x Ph pixels, sub-samples in 8x4 blocks, lanes refilled from the item ------------------------
             unsigned *acc = acc_all + (threadIdx.x >> 5) * (P * p.Ph * 3);
             const int sw = pw * f, sh = ph * f;
@@ -424,6 +457,7 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
                 __syncwarp();
             }
         }
+      }
     }
 
     const unsigned v0 = __reduce_add_sync(0xffffffffu, cnt.primary);
