@@ -27,14 +27,14 @@ def part_ms(rank, n):
     return best
 
 
-for strip in (0, 32, 16, 8, 4, 2):
+for strip in (0, 8, 4, 2):
     L.rt_set_partition(0, strip)
     full = part_ms(0, 1)
     print(f"full frame, strip width {strip or 'default'}: {full:.2f} ms", flush=True)
 L.rt_set_partition(0, 0)
 full = part_ms(0, 1)
-for band_rows in (1, 4, 16):
-    for strip in (16, 8, 4, 2):
+for band_rows in (1, 4):
+    for strip in (8, 4, 2):
         L.rt_set_partition(band_rows, strip)
         ms = [part_ms(r, world) for r in range(world)]
         print(f"world {world} band_rows {band_rows:2d} strip {strip or 'default':>7}: max {max(ms):.2f} mean {sum(ms) / world:.2f} ms; ideal {full / world:.2f}; "
