@@ -159,6 +159,9 @@ typedef struct RtScene RtScene; /* opaque */
  * reference-order tie ranks.  opts may be NULL. */
 int rt_scene_create(const RtSceneDesc *desc, const RtBuildOptions *opts, RtScene **out);
 void rt_scene_destroy(RtScene *scene);
+/* The library keeps a few device blocks of destroyed scenes and finished builds per GPU and reuses them, so that creating
+ * scene after scene makes no cudaMalloc / cudaFree call; rt_trim() gives them back to the driver. */
+int rt_trim(void);
 int rt_scene_info(const RtScene *scene, RtSceneInfo *info);
 
 /* Replaces RayTracer::render + ImageProcessor::downSample

@@ -61,6 +61,7 @@ struct RtScene {
     int refill_threshold = 0;
     int max_ctas_per_sm = 0;  // experiments: 0 = occupancy limit
     void *arena = nullptr;
+    size_t arena_cap = 0;
     SceneBuffers buf;
     RenderSlot slot[kFrameSlots];
     unsigned char *d_parts = nullptr;  // rt_render_multi / rt_render_part_to_host: this device's packed bands
@@ -420,7 +421,9 @@ int scene_create_impl(const RtSceneDesc *desc, const RtBuildOptions *opts, RtSce
     const float leaf_cost = (opts && opts->ploc_leaf_cost > 0) ? opts->ploc_leaf_cost : 1.0f;  // tools/ploc_tune.py: 1.0 beats 1.6 and 2.5
     rc = build.run(*desc, builder, radius, leaf_cost, s->n_sms, s->stream, s->buf, err);
     s->arena = build.arena;
+    s->arena_cap = build.arena_bytes;
     build.arena = nullptr;
+    if (rc != 0) cudaStreamSynchronize(s->stream);  // nothing may still be running in the blocks that go back to the cache
     if (!keep_build) build.release_scratch();
     if (rc != 0) return bail(rc == -2 ? RT_ERR_STATE : RT_ERR_CUDA, "scene build: " + err);
     for (int i = 0; i < 2; i++)
@@ -571,6 +574,12 @@ int rt_warmup(int device) {
     CU(cudaFree(nullptr));
     int occ[2], warps;
     if (render_kernel_v2_occupancy(occ, &warps) != 0) return fail(RT_ERR_CUDA, "render kernel cannot be loaded on this device (built for sm_100a)");
+    return RT_OK;
+}
+
+// frees the device blocks kept for reuse by later rt_scene_create calls (scene_build.h block cache)
+int rt_trim(void) {
+    block_cache_trim();
     return RT_OK;
 }
 
@@ -805,7 +814,7 @@ void rt_scene_destroy(RtScene *s) {
     g.use(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
-    cudaFree(s->arena);
+    block_release(s->arena, s->arena_cap);  // the streams are drained: the block may be handed to the next scene
     cudaFree(s->d_parts);
     for (auto &sl: s->slot) {
         cudaFree(sl.d_frame);

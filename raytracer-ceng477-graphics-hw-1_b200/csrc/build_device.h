@@ -100,8 +100,10 @@ constexpr int kRefLevels = 21;  // depth cap 19 (bvh.h:18) -> at most 20 levels 
 size_t ref_scratch_bytes(int np);
 // enqueues the whole build on `stream`: writes ranks[8][np], ref_nodes (float4[3] per node), ref_leaf_prims and the
 // statistics fields of *result
-void enqueue_reference_tree(const Aabb *bounds, const float *key, int np, const RefScratch &s, uint32_t *ranks,
-                            float4 *ref_nodes, int *ref_leaf_prims, BuildResult *result, int n_sms, cudaStream_t stream);
+// (`grid` = co-resident CTAs of the cooperative level loop, ref_max_grid; returns a cudaError_t as int)
+int ref_max_grid(int n_sms);
+int enqueue_reference_tree(const Aabb *bounds, const float *key, int np, const RefScratch &s, uint32_t *ranks,
+                           float4 *ref_nodes, int *ref_leaf_prims, BuildResult *result, int grid, cudaStream_t stream);
 
 // ---- candidate trees ------------------------------------------------------------------------------------------
 struct MortonScratch {
@@ -146,7 +148,7 @@ struct SahScratch {
     int *root_ref;
 };
 constexpr int kSahLevels = 64;
-void enqueue_sah(const Aabb *bounds, int n, const SahScratch &s, DevTree &out, const BuildResult *res, int n_sms,
-                 cudaStream_t stream);
+int sah_max_grid(int n_sms);
+int enqueue_sah(const Aabb *bounds, int n, const SahScratch &s, DevTree &out, const BuildResult *res, int grid, cudaStream_t stream);
 
 }  // namespace rtb

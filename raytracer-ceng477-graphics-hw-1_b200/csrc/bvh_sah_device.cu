@@ -12,9 +12,12 @@
 #include <cfloat>
 #include <cstdint>
 
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include "build_device.h"
+
+namespace cg = cooperative_groups;
 
 namespace rtb {
 
@@ -86,7 +89,13 @@ __global__ void sah_init_kernel(int n, SahScratch s) {
     }
 }
 
-__global__ void __launch_bounds__(kT) sah_level_kernel(const Aabb *bounds, SahScratch sc, int level, HostNode *nodes) {
+// All levels in ONE cooperative launch: persistent CTAs stride over the open ranges of a level, a grid barrier separates
+// the levels, the loop ends when a level leaves no open range (round 1 launched one kernel per level and read the
+// range count back to the host in between).
+__global__ void __launch_bounds__(kT) sah_build_kernel(const Aabb *bounds, SahScratch sc, HostNode *nodes) {
+    cg::grid_group grid = cg::this_grid();
+  for (int level = 0; level < kSahLevels; level++) {
+    if (__ldcg(&sc.level_count[level]) == 0) break;  // the same value in every CTA: written before the last grid barrier
     __shared__ SBox s_box, s_cbox, s_left, s_right;
     __shared__ SBox s_bins[3][kBins];
     __shared__ int s_cnt[3][kBins];
@@ -95,7 +104,7 @@ __global__ void __launch_bounds__(kT) sah_level_kernel(const Aabb *bounds, SahSc
     __shared__ float s_c0, s_scale;
 
     const int t = threadIdx.x;
-    const int n_tasks = sc.level_count[level];
+    const int n_tasks = __ldcg(&sc.level_count[level]);
     const SahTask *tasks = sc.queue[level & 1];
     SahTask *next = sc.queue[(level + 1) & 1];
     int *n_next = &sc.level_count[level + 1];
@@ -253,6 +262,8 @@ __global__ void __launch_bounds__(kT) sah_level_kernel(const Aabb *bounds, SahSc
         }
     }
   }
+    grid.sync();
+  }
 }
 
 // the whole scene is one leaf (or one primitive): give it a parent so that node 0 always exists
@@ -275,16 +286,23 @@ __global__ void sah_fixup_kernel(SahScratch s, HostNode *nodes, const BuildResul
 
 }  // namespace
 
-void enqueue_sah(const Aabb *bounds, int n, const SahScratch &s, DevTree &out, const BuildResult *res, int n_sms,
-                 cudaStream_t stream) {
+int sah_max_grid(int n_sms) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sah_build_kernel, kT, 0) != cudaSuccess || per_sm < 1) return 1;
+    return n_sms * per_sm;
+}
+
+int enqueue_sah(const Aabb *bounds, int n, const SahScratch &s, DevTree &out, const BuildResult *res, int grid, cudaStream_t stream) {
     sah_init_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, s);
-    for (int level = 0; level < kSahLevels; level++) {
-        long long open = level < 30 ? (1LL << level) : (1LL << 30);
-        if (open > n) open = n;
-        const long long cap = (long long) n_sms * 8;
-        sah_level_kernel<<<(unsigned) (open < cap ? open : cap), kT, 0, stream>>>(bounds, s, level, out.nodes);
-    }
+    long long want = n < grid ? n : grid;  // never more CTAs than primitives (a level has at most n / 2 open ranges)
+    if (want < 1) want = 1;
+    SahScratch sc = s;
+    HostNode *nodes = out.nodes;
+    void *args[] = {&bounds, &sc, &nodes};
+    const cudaError_t e = cudaLaunchCooperativeKernel((void *) sah_build_kernel, dim3((unsigned) want), dim3(kT), args, 0, stream);
+    if (e != cudaSuccess) return (int) e;
     sah_fixup_kernel<<<1, 1, 0, stream>>>(s, out.nodes, res, out.status);
+    return (int) cudaGetLastError();
 }
 
 }  // namespace rtb

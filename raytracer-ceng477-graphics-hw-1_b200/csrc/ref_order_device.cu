@@ -6,16 +6,19 @@
 // order inside a leaf is visit order), then one thread per primitive walks from the root to its leaf and
 // accumulates, for each of the 8 direction-sign octants, how many primitives the reference visits before it.
 //
-// No host round trip: the number of open nodes of a level lives in device memory; the kRefLevels level kernels are
-// enqueued back to back with persistent CTAs that stride over however many tasks the previous level left, and the
-// nodes are written straight into the replay layout (rt_internal.h `ref_nodes`).
+// No host round trip: ONE cooperative launch runs all levels — the number of open nodes of a level lives in device
+// memory, persistent CTAs stride over however many tasks the previous level left, a grid barrier separates the levels —
+// and the nodes are written straight into the replay layout (rt_internal.h `ref_nodes`).
 #include <cfloat>
 #include <cstdint>
 #include <vector>
 
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include "build_device.h"
+
+namespace cg = cooperative_groups;
 
 namespace rtb {
 
@@ -50,12 +53,16 @@ __global__ void ref_init_kernel(int np, RefScratch s, BuildResult *res) {
     }
 }
 
-__global__ void __launch_bounds__(kT) ref_level_kernel(const Aabb *bounds, const float *key, int np, RefScratch s, int level,
-                                                        float4 *ref_nodes, BuildResult *res) {
+// all levels in ONE cooperative launch (grid barrier between levels, the loop ends with the first empty level)
+__global__ void __launch_bounds__(kT) ref_build_kernel(const Aabb *bounds, const float *key, int np, RefScratch s, float4 *ref_nodes,
+                                                        BuildResult *res) {
+    cg::grid_group grid = cg::this_grid();
+  for (int level = 0; level < kRefLevels; level++) {
+    if (__ldcg(&s.level_count[level]) == 0) break;
     __shared__ unsigned s_mn[3], s_mx[3];
     __shared__ int s_scan[kT];
     const int t = threadIdx.x;
-    const int n_tasks = s.level_count[level];
+    const int n_tasks = __ldcg(&s.level_count[level]);
     const RefTask *tasks = s.queue[level & 1];
     RefTask *next = s.queue[(level + 1) & 1];
     int *ids = s.ids, *tmp = s.tmp;
@@ -148,6 +155,8 @@ __global__ void __launch_bounds__(kT) ref_level_kernel(const Aabb *bounds, const
             }
         }
     }
+    grid.sync();
+  }
 }
 
 // raytracer.cpp:190-196: at an inner node the left child is visited first iff direction[axis] > 0
@@ -180,17 +189,24 @@ __global__ void ref_ranks_kernel(RefScratch s, int np, uint32_t *ranks, int *ref
 
 }  // namespace
 
-void enqueue_reference_tree(const Aabb *bounds, const float *key, int np, const RefScratch &s, uint32_t *ranks,
-                            float4 *ref_nodes, int *ref_leaf_prims, BuildResult *result, int n_sms, cudaStream_t stream) {
-    if (np <= 0) return;
+int ref_max_grid(int n_sms) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ref_build_kernel, kT, 0) != cudaSuccess || per_sm < 1) return 1;
+    return n_sms * per_sm;
+}
+
+int enqueue_reference_tree(const Aabb *bounds, const float *key, int np, const RefScratch &s, uint32_t *ranks, float4 *ref_nodes,
+                           int *ref_leaf_prims, BuildResult *result, int grid, cudaStream_t stream) {
+    if (np <= 0) return 0;
     ref_init_kernel<<<(np + 255) / 256, 256, 0, stream>>>(np, s, result);
-    for (int level = 0; level < kRefLevels; level++) {
-        long long open = level < 30 ? (1LL << level) : (1LL << 30);  // at most 2^level open nodes
-        if (open > np) open = np;
-        const long long cap = (long long) n_sms * 8;
-        ref_level_kernel<<<(unsigned) (open < cap ? open : cap), kT, 0, stream>>>(bounds, key, np, s, level, ref_nodes, result);
-    }
+    long long want = np < grid ? np : grid;
+    if (want < 1) want = 1;
+    RefScratch sc = s;
+    void *args[] = {&bounds, &key, &np, &sc, &ref_nodes, &result};
+    const cudaError_t e = cudaLaunchCooperativeKernel((void *) ref_build_kernel, dim3((unsigned) want), dim3(kT), args, 0, stream);
+    if (e != cudaSuccess) return (int) e;
     ref_ranks_kernel<<<(np + 255) / 256, 256, 0, stream>>>(s, np, ranks, ref_leaf_prims, result);
+    return (int) cudaGetLastError();
 }
 
 }  // namespace rtb

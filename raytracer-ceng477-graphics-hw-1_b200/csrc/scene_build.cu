@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -474,8 +475,94 @@ double now_ms() {
 
 }  // namespace
 
+// ---- block cache ----------------------------------------------------------------------------------------------
+namespace {
+struct CachedBlock {
+    int device;
+    void *ptr;
+    size_t cap;
+};
+std::mutex g_cache_mutex;
+std::vector<CachedBlock> g_cache;
+constexpr size_t kCacheBlocksPerDevice = 6;
+}  // namespace
+
+void *block_acquire(size_t bytes, size_t *cap) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mutex);
+        int best = -1;
+        for (size_t i = 0; i < g_cache.size(); i++)
+            if (g_cache[i].device == dev && g_cache[i].cap >= bytes && g_cache[i].cap <= 4 * bytes + (1 << 20) &&
+                (best < 0 || g_cache[i].cap < g_cache[(size_t) best].cap))
+                best = (int) i;
+        if (best >= 0) {
+            void *p = g_cache[(size_t) best].ptr;
+            *cap = g_cache[(size_t) best].cap;
+            g_cache.erase(g_cache.begin() + best);
+            return p;
+        }
+    }
+    void *p = nullptr;
+    const size_t want = (bytes + (1 << 16)) & ~(size_t) ((1 << 16) - 1);  // a little headroom so that similar scenes reuse it
+    if (cudaMalloc(&p, want) != cudaSuccess) {
+        cudaGetLastError();
+        block_cache_trim();  // give the cached blocks back and try once more
+        if (cudaMalloc(&p, want) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+    }
+    *cap = want;
+    return p;
+}
+
+void block_release(void *ptr, size_t cap) {
+    if (!ptr) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    void *evict = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mutex);
+        size_t mine = 0;
+        int smallest = -1;
+        for (size_t i = 0; i < g_cache.size(); i++)
+            if (g_cache[i].device == dev) {
+                mine++;
+                if (smallest < 0 || g_cache[i].cap < g_cache[(size_t) smallest].cap) smallest = (int) i;
+            }
+        if (mine >= kCacheBlocksPerDevice) {  // full: keep the larger blocks
+            if (g_cache[(size_t) smallest].cap < cap) {
+                evict = g_cache[(size_t) smallest].ptr;
+                g_cache[(size_t) smallest] = CachedBlock{dev, ptr, cap};
+            } else {
+                evict = ptr;
+            }
+        } else {
+            g_cache.push_back(CachedBlock{dev, ptr, cap});
+        }
+    }
+    if (evict) cudaFree(evict);
+}
+
+void block_cache_trim() {
+    std::vector<CachedBlock> all;
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mutex);
+        all.swap(g_cache);
+    }
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (auto &b: all) {
+        cudaSetDevice(b.device);
+        cudaFree(b.ptr);
+    }
+    cudaSetDevice(prev);
+}
+
 void SceneBuild::release_scratch() {
-    if (scratch) cudaFree(scratch);
+    if (scratch) block_release(scratch, scratch_bytes);
     scratch = nullptr;
 }
 
@@ -494,10 +581,12 @@ int SceneBuild::run(const RtSceneDesc &d, int builder, int ploc_radius, float pl
     Scratch dummy_s = Scratch();
     carve_scene(size_scene, dummy_o, d);
     carve_scratch(size_scratch, dummy_s, d, builder, ploc_grid);
-    CKB(cudaMalloc(&arena, size_scene.off + 256));
-    CKB(cudaMalloc(&scratch, size_scratch.off + 256));
-    arena_bytes = size_scene.off + 256;
-    scratch_bytes = size_scratch.off + 256;
+    arena = block_acquire(size_scene.off + 256, &arena_bytes);
+    scratch = block_acquire(size_scratch.off + 256, &scratch_bytes);
+    if (!arena || !scratch) {
+        err = "out of device memory";
+        return -1;
+    }
     Bump bs, bx;
     bs.base = (char *) arena;
     bx.base = (char *) scratch;
@@ -549,7 +638,14 @@ int SceneBuild::run(const RtSceneDesc &d, int builder, int ploc_radius, float pl
         PrepArgs pa = {s.vertices, s.triangles, s.spheres, nt, ns, s.bounds, s.key, s.rec, out.prim_bounds, out.tri_nm, out.tri_nn,
                        out.sph_cr, out.sph_mat, out.result};
         prep_kernel<<<(np + T - 1) / T, T, 0, stream>>>(pa);
-        enqueue_reference_tree(s.bounds, s.key, np, s.ref, out.ranks, out.ref_nodes, out.ref_leaf_prims, out.result, n_sms, stream);
+        {
+            const int e = enqueue_reference_tree(s.bounds, s.key, np, s.ref, out.ranks, out.ref_nodes, out.ref_leaf_prims, out.result,
+                                                 ref_max_grid(n_sms), stream);
+            if (e != 0) {
+                err = std::string("reference tree launch: ") + cudaGetErrorString((cudaError_t) e);
+                return -1;
+            }
+        }
         if (np == 1) {
             single_prim_tree_kernel<<<1, 1, 0, stream>>>(s.bounds, s.tree[0]);
             n_candidates = 1;
@@ -576,7 +672,11 @@ int SceneBuild::run(const RtSceneDesc &d, int builder, int ploc_radius, float pl
                 DevTree &t = s.tree[builder == RT_BUILD_AUTO ? 1 : 0];
                 s.sah.n_nodes = t.n_used;  // the builder's node counter IS the tree's used-slot count
                 t.prim_order = s.sah.ids;  // ... and the index array it partitions IS the leaf order
-                enqueue_sah(s.bounds, np, s.sah, t, out.result, n_sms, stream);
+                const int e = enqueue_sah(s.bounds, np, s.sah, t, out.result, sah_max_grid(n_sms), stream);
+                if (e != 0) {
+                    err = std::string("SAH builder launch: ") + cudaGetErrorString((cudaError_t) e);
+                    return -1;
+                }
                 n_candidates = builder == RT_BUILD_AUTO ? 2 : 1;
             }
         }

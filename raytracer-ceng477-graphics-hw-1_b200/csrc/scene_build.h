@@ -25,10 +25,18 @@ struct SceneBuffers {
     uint32_t *ranks = nullptr;
 };
 
+// Device blocks of finished builds and destroyed scenes are kept per device and handed out again (first fit within 4x
+// the requested size): creating scene after scene — a dynamic scene rebuilt every frame — then makes no cudaMalloc /
+// cudaFree call at all (both cost milliseconds on a busy box, and cudaFree synchronises the device).  rt_trim() frees
+// the cache.
+void *block_acquire(size_t bytes, size_t *cap);   // nullptr on failure
+void block_release(void *ptr, size_t cap);
+void block_cache_trim();
+
 struct SceneBuild {
     void *arena = nullptr;    // persistent: owned by the RtScene afterwards
     void *scratch = nullptr;  // builders' scratch: released by release_scratch()
-    size_t arena_bytes = 0, scratch_bytes = 0;
+    size_t arena_bytes = 0, scratch_bytes = 0;  // capacities of the two blocks (block_acquire)
     BuildResult result;       // host copy of the device result block
     bool used_host_builder = false;
     float ms_device = 0;            // CUDA events around uploads + every build kernel
