@@ -995,6 +995,7 @@ int rt_render_multi(RtScene *const *scenes, int n, const RtCamera *cam, int aa, 
     const bool pinned_dst = is_pinned(rgb_out);
     if (!pinned_dst) {
         if (g.use(root->device) != 0) return fail(RT_ERR_CUDA, "cudaSetDevice failed");
+        if (root->slot[0].busy) return fail(RT_ERR_STATE, "rt_render_multi into pageable memory while an asynchronous frame is in flight");
         int rc = ensure(&root->slot[0].h_pinned, &root->slot[0].pinned_cap, bytes, true);
         if (rc != RT_OK) return rc;
         frame = root->slot[0].h_pinned;

@@ -100,6 +100,27 @@ def test_bands_equal_full_frame(aa):
             assert np.array_equal(mine[r * stride:r * stride + want.size], want), (world, r)
 
 
+@pytest.mark.parametrize("aa,w,h", [(24, 37, 19), (40, 9, 7), (8, 131, 67), (16, 97, 33)])
+def test_register_accumulator_factors(aa, w, h):
+    """AA factors that are multiples of 8 but not powers of two (24: 3 x 6 blocks of 8x4 sub-samples per pixel; 40: 5 x 10)
+    and frames narrower than a 32-pixel block column, through the guided-scheduling kernel, whole and in 3 parts."""
+    import torch
+    sc = H.golden_scene("simple_reflectance")
+    cam = sc.camera(0, w, h)
+    orc = H.OracleScene(sc)
+    want, ost = orc.render(cam, aa)
+    orc.close()
+    rt = tracer("simple_reflectance")
+    got = rt.render(cam, aa)
+    assert np.array_equal(want, got), H.diff_report(want, got)
+    assert rt.last_stats.total_rays == ost.total_rays
+    frame = torch.zeros(w * h * 3, dtype=torch.uint8, device="cuda")
+    for r in range(3):
+        rt.render_part_into_frame(cam, aa, r, 3, frame.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(frame.cpu().numpy().reshape(want.shape), want)
+
+
 def test_render_async_overlaps_cameras():
     """rt_render_async / rt_wait (the multi-camera path, raytracer.cpp:505-519): three cameras in flight on one handle,
     page-locked and pageable destinations, results equal the synchronous call; a fourth frame in flight is refused."""
