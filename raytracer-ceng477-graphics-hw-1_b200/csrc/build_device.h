@@ -146,6 +146,7 @@ struct SahScratch {
     int *level_count;     // [kSahLevels + 2]
     int *n_nodes;         // allocated nodes
     int *root_ref;
+    int cap_tasks, cap_nodes;  // extents of the queues / node array (bounds-checked builds)
 };
 constexpr int kSahLevels = 64;
 int sah_max_grid(int n_sms);

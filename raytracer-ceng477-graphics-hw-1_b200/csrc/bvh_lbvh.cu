@@ -148,6 +148,7 @@ __global__ void radix_tree_kernel(const unsigned long long *keys, int n, TreeNod
         if (t == 1) break;
     }
     const int gamma = i + s * d + min(d, 0);
+    RT_CHECK(gamma >= 0 && gamma + 1 < n && j >= 0 && j < n);
     const int lo = min(i, j), hi = max(i, j);
     TreeNode nd;
     nd.first = lo;
@@ -410,10 +411,12 @@ ploc_kernel(const unsigned long long *keys, const Aabb *bounds, int n, PlocNode 
                 }
                 nd.cost = c_split;
                 id = n_alloc + off_new++;
+                RT_CHECK(id >= n && id < 2 * n - 1 && l >= 0 && l < id && r >= 0 && r < id);
                 nodes[id] = nd;
                 nodes[l].parent = id;
                 nodes[r].parent = id;
             }
+            RT_CHECK(off_keep >= 0 && off_keep < m);
             cout[off_keep++] = id;
         }
         n_alloc += all_new;
@@ -449,6 +452,7 @@ __global__ void ploc_order_kernel(const unsigned long long *keys, int n, const P
         if (nodes[par].right == cur) pos += nodes[nodes[par].left].size;
         cur = par;
     }
+    RT_CHECK(pos >= 0 && pos < n);
     first_of[id] = pos;
     if (id < n) prim_order[pos] = (int) (unsigned) keys[id];
 }
@@ -473,6 +477,7 @@ __global__ void ploc_emit_kernel(int n, const PlocNode *nodes, const int *first_
         if (c == 0) h.child0 = ref;
         else h.child1 = ref;
     }
+    RT_CHECK((2 * n - 2) - id >= 0 && (2 * n - 2) - id < n - 1);
     out[(2 * n - 2) - id] = h;
 }
 

@@ -224,6 +224,7 @@ __global__ void __launch_bounds__(kT) sah_build_kernel(const Aabb *bounds, SahSc
         int r = lo + n_left + (s_scan[t] - (my_cnt - my_left));
         for (int i = lo + t; i < hi; i += kT) {
             const int id = ids[i];
+            RT_CHECK(id >= 0 && l >= lo && l <= hi && r >= lo && r <= hi);
             if (bin_of(bounds[id], axis, c0, scale) <= best_bin) tmp[l++] = id;
             else tmp[r++] = id;
         }
@@ -257,6 +258,7 @@ __global__ void __launch_bounds__(kT) sah_build_kernel(const Aabb *bounds, SahSc
                 else nd.child1 = ref;
             } else {
                 const int slot = atomicAdd(n_next, 1);
+                RT_CHECK(slot >= 0 && slot <= sc.cap_tasks && me >= 0 && me < sc.cap_nodes);
                 next[slot] = SahTask{me, c, los[c], his[c]};
             }
         }

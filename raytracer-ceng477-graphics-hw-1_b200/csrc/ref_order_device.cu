@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(kT) ref_build_kernel(const Aabb *bounds, const
             __syncthreads();
             for (int i = b0; i < b1; i++) {
                 const int id = ids[i];
+                RT_CHECK(id >= 0 && id < np && l >= lo && l <= hi && r >= lo && r <= hi);
                 if (k[id] < mid) tmp[l++] = id;
                 else tmp[r++] = id;
             }
@@ -129,6 +130,7 @@ __global__ void __launch_bounds__(kT) ref_build_kernel(const Aabb *bounds, const
             if (t == 0) {
                 left = atomicAdd(s.n_nodes, 2);
                 const int slot = atomicAdd(&s.level_count[level + 1], 2);
+                RT_CHECK(slot >= 0 && slot + 1 <= np && left >= 1 && left + 1 <= 2 * np);
                 next[slot] = RefTask{left, lo, lo + n_left, task.depth + 1};
                 next[slot + 1] = RefTask{left + 1, lo + n_left, hi, task.depth + 1};
             }

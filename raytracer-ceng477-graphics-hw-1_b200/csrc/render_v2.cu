@@ -113,6 +113,7 @@ RT_DEV bool trace_step(const RenderParams &p, Lane &L, const LaneStacks &S, V3 I
                 // "while-while": lanes keep descending until every lane of the warp holds a leaf (or is done), then
                 // the warp runs the primitive tests together
                 while ((unsigned) node < (unsigned) kSentinel) {
+                    RT_CHECK((node & 3) == 0 && (node >> 2) < p.n_nodes && sp >= S.stack && sp < S.stack + kStackSize);
                     const float4 *nd = nodes + (unsigned) node;
                     float4 n0, n1, n2, n3;
                     ld256(nd, n0, n1);
@@ -144,6 +145,7 @@ RT_DEV bool trace_step(const RenderParams &p, Lane &L, const LaneStacks &S, V3 I
                 if (node < 0) {
                     const int enc = ~node;
                     const int first = enc >> 3, count = (enc & 7) + 1;
+                    RT_CHECK(first >= 0 && first + count <= p.n_prims + 1 && sp > S.stack);
                     node = *--sp;
                     for (int s = first; s < first + count; s++) {
                         float t;
@@ -244,6 +246,7 @@ RT_DEV bool trace_step(const RenderParams &p, Lane &L, const LaneStacks &S, V3 I
         } else {
             const float4 m1 = __ldg(&p.materials[4 * (L.mat - 1) + 1]);
             if (__float_as_int(m1.w) != 0) {  // mirror: raytracer.cpp:430-439
+                RT_CHECK(L.npush >= 0 && L.npush <= kMaxSupportedDepth);
                 S.local_stack[L.npush] = L.color;
                 S.mat_stack[L.npush] = L.mat;
                 L.npush++;
@@ -280,6 +283,7 @@ RT_DEV bool trace_step(const RenderParams &p, Lane &L, const LaneStacks &S, V3 I
 }
 
 RT_DEV unsigned char *pixel_ptr(const RenderParams &p, int local_band, int y_in_band, int px, int py) {
+    RT_CHECK(px >= 0 && px < p.nx && py >= 0 && py < p.ny && local_band >= 0 && local_band < p.n_bands && y_in_band >= 0 && y_in_band < p.Ph);
     if (p.out_mode == kOutFrame) return p.out + ((size_t) py * p.nx + px) * 3;
     return p.out + (((size_t) local_band * p.Ph + y_in_band) * p.nx + px) * 3;
 }
@@ -358,6 +362,7 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
                 if (lane == pix) mine = R | (G << 8) | (B << 16);
             }
             unsigned char *o = p.out_mode == kOutFrame ? p.out + ((size_t) y * p.nx + x) * 3 : p.out + ((size_t) local_row * p.nx + x) * 3;
+            RT_CHECK(!valid || (x >= 0 && x < p.nx && y >= 0 && y < p.ny && local_row >= 0 && local_row < p.n_bands));
             // an aligned run of 4k pixels of one row leaves as 3k 32-bit words built with two shuffles each
             // (word w = bytes 4w .. 4w+3 = pixels (4w)/3 and (4w)/3 + 1, shifted by w % 3 bytes)
             const bool whole = (n & 3u) == 0u && (start & (n - 1u)) == 0u && __all_sync(0xffffffffu, valid || lane >= (int) n);
@@ -436,6 +441,7 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
                         o[1] = (unsigned char) g8;
                         o[2] = (unsigned char) b8;
                     } else {
+                        RT_CHECK(((ly / f) * pw + (lx / f)) < P * p.Ph);
                         unsigned *a = &acc[((ly / f) * pw + (lx / f)) * 3];
                         atomicAdd(a, r8);
                         atomicAdd(a + 1, g8);

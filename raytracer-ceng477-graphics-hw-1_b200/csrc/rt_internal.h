@@ -6,6 +6,17 @@
 
 #include "rt_b200.h"
 
+// Bounds-checked build (tools/build_variants.sh checked:-DRT_BOUNDS_CHECK; tests/test_gpu_parity.py::
+// test_bounds_checked_build runs it in a subprocess): every computed index of the kernels is asserted against the extent
+// of the array it goes into.  compute-sanitizer is closed on the GPU pool this was developed on, so this is the memory-
+// safety evidence; in the product build the macro compiles to nothing.
+#ifdef RT_BOUNDS_CHECK
+#include <cassert>
+#define RT_CHECK(cond) assert(cond)
+#else
+#define RT_CHECK(cond) ((void) 0)
+#endif
+
 namespace rtb {
 
 // ---------------------------------------------------------------------------------------------

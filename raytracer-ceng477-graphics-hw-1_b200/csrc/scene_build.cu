@@ -66,6 +66,7 @@ __global__ void prep_kernel(PrepArgs a) {
     const bool live = i < np;
     if (live && i < a.nt) {
         const RtTriangle t = a.triangles[i];
+        RT_CHECK(t.v0_id >= 1 && t.v1_id >= 1 && t.v2_id >= 1);
         const float3 p = ld_vertex(a.vertices, t.v0_id), q = ld_vertex(a.vertices, t.v1_id), r = ld_vertex(a.vertices, t.v2_id);
         const float vx[3] = {p.x, q.x, r.x}, vy[3] = {p.y, q.y, r.y}, vz[3] = {p.z, q.z, r.z};
         for (int k = 0; k < 3; k++) {  // parser.h:272-296
@@ -164,6 +165,7 @@ __global__ void tree_parents_kernel(DevTree t) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (*t.status != 0 || i >= *t.n_used) return;
     const int c0 = t.nodes[i].child0, c1 = t.nodes[i].child1;
+    RT_CHECK((!is_inner(c0) || c0 < t.cap) && (!is_inner(c1) || c1 < t.cap));
     if (is_inner(c0)) t.parent[c0] = (i << 1);
     if (is_inner(c1)) t.parent[c1] = (i << 1) | 1;
 }
@@ -211,6 +213,7 @@ __global__ void tree_reduce_kernel(DevTree t) {
         const int pp = t.parent[cur];
         if (pp < 0) return;
         cur = pp >> 1;
+        RT_CHECK(cur >= 0 && cur < t.cap);
         if (atomicAdd(&t.arrivals[cur], 1) != 1) return;  // the sibling subtree is not finished yet
     }
 }
@@ -314,6 +317,9 @@ __global__ void layout_kernel(LayoutArgs a) {
     const int first_count = nd.child0 >= 0 ? t.count[nd.child0] : 0;
     const int r0 = nd.child0 >= 0 ? 4 * (idx + 1) : nd.child0;
     const int r1 = nd.child1 >= 0 ? 4 * (idx + 1 + first_count) : nd.child1;
+    RT_CHECK(idx >= 0 && idx < a.res->n_nodes[a.res->chosen] && idx < (a.np > 1 ? a.np : 1));
+    RT_CHECK(nd.child0 >= 0 || ((~nd.child0) >> 3) + ((~nd.child0) & 7) + 1 <= a.np + 1);
+    RT_CHECK(nd.child1 >= 0 || ((~nd.child1) >> 3) + ((~nd.child1) & 7) + 1 <= a.np + 1);
     float4 *o = a.nodes + 4 * (size_t) idx;
     o[0] = make_float4(c0[0], h0[0], c0[1], h0[1]);
     o[1] = make_float4(c1[0], h1[0], c1[1], h1[1]);
@@ -331,6 +337,7 @@ __global__ void place_prims_kernel(LayoutArgs a, const float4 *rec, float4 *prim
     }
     if (*t.status != 0) return;
     const int id = t.prim_order[s];
+    RT_CHECK(id >= 0 && id < a.np);
     for (int k = 0; k < 3; k++) prims[3 * (size_t) s + k] = rec[3 * (size_t) id + k];
     slot_of_prim[id] = s;
 }
@@ -426,6 +433,8 @@ void carve_scratch(Bump &b, Scratch &s, const RtSceneDesc &d, int builder, int p
         s.sah.level_count = b.take<int>(kSahLevels + 2);
         s.sah.n_nodes = b.take<int>(1);
         s.sah.root_ref = b.take<int>(1);
+        s.sah.cap_tasks = cap;
+        s.sah.cap_nodes = cap + 1;
     }
     carve_tree(b, s.tree[0], cap + 1, cap);
     if (builder == RT_BUILD_AUTO) carve_tree(b, s.tree[1], cap + 1, cap);

@@ -537,3 +537,20 @@ def test_two_million_triangle_scene(builder):
     rt.render(big, 1)
     print(f"   1440x720: {rt.last_stats.ms_render:.2f} ms, {rt.last_stats.total_rays / rt.last_stats.ms_render / 1e3:.0f} Mrays/s")
     rt.close()
+
+
+def test_bounds_checked_build():
+    """Memory safety without compute-sanitizer (closed on this GPU pool): the library built with -DRT_BOUNDS_CHECK asserts
+    every computed index of the render kernel and of the builders against the extent of its array.  tools/
+    checked_build_run.py drives that build (ab/checked.so, made by __graft_entry__.build()) over ~130 cases in a
+    subprocess — a fired assert would take the CUDA context down with it."""
+    import os
+    import subprocess
+    import sys
+    lib = os.path.join(H.PKG, "ab", "checked.so")
+    if not os.path.exists(lib):
+        pytest.skip("ab/checked.so not built")
+    p = subprocess.run([sys.executable, os.path.join(H.ROOT, "tools", "checked_build_run.py")], capture_output=True, text=True, timeout=900)
+    print(p.stdout[-500:], p.stderr[-2000:])
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert "no assertion fired" in p.stdout
