@@ -181,6 +181,12 @@ int rt_render(RtScene *scene, const RtCamera *cam, int aa_factor, unsigned char 
 int rt_render_async(RtScene *scene, const RtCamera *cam, int aa_factor, unsigned char *rgb_out, int *ticket);
 int rt_wait(RtScene *scene, int ticket, RtStats *stats);
 
+/* When rgb_out is page-locked (rt_host_alloc, cudaHostAlloc, cudaHostRegister) and the frame is large (>= 32 MB by
+ * default), rt_render / rt_render_async let the kernel store finished pixels straight into it over PCIe instead of rendering
+ * into device memory and copying afterwards.  rt_set_zero_copy(min_frame_bytes) moves that threshold for the whole
+ * process (negative = never). */
+int rt_set_zero_copy(int64_t min_frame_bytes);
+
 /* Page-locked host memory for frames (cudaMallocHost / cudaFreeHost). */
 int rt_host_alloc(int64_t bytes, void **ptr);
 int rt_host_free(void *ptr);

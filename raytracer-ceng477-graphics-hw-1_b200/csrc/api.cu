@@ -205,6 +205,11 @@ constexpr long long kNominalWarps = 148LL * 7 * 4;  // resident warps of one B20
 
 // experiments (rt_set_partition): 0 = the defaults computed below
 int g_band_rows = 0, g_strip_width = 0;
+// rt_render / rt_render_async into page-locked memory: frames of at least this many bytes are written by the kernel itself
+// (rt_set_zero_copy).  Measured (tools/e2e_zero_copy.py): the kernel's stores cross PCIe at ~15 GB/s against ~32 GB/s for
+// the copy engine, so it only pays when the kernel runs much longer than the transfer — 8K 16x: 655.9 -> 654.6 ms,
+// horse_and_mug 1440x720: 0.468 -> 0.446 ms, but simple 800x800: 0.104 -> 0.151 ms.
+long long g_zero_copy_min = 32LL << 20;
 
 ItemGeom item_geometry(const RtCamera *cam, int aa, int world) {
     ItemGeom g;
@@ -577,6 +582,13 @@ int rt_warmup(int device) {
     return RT_OK;
 }
 
+// tuning: smallest frame (bytes) that rt_render / rt_render_async let the kernel write straight into a page-locked
+// destination; negative = always render into device memory and copy afterwards
+int rt_set_zero_copy(int64_t min_frame_bytes) {
+    g_zero_copy_min = min_frame_bytes;
+    return RT_OK;
+}
+
 // frees the device blocks kept for reuse by later rt_scene_create calls (scene_build.h block cache)
 int rt_trim(void) {
     block_cache_trim();
@@ -880,22 +892,31 @@ int rt_render_async(RtScene *s, const RtCamera *cam, int aa, unsigned char *rgb_
     rc = slot_prepare(sl);
     if (rc != RT_OK) return rc;
     const size_t bytes = (size_t) cam->image_width * cam->image_height * 3;
-    rc = ensure(&sl.d_frame, &sl.frame_cap, bytes, false);
-    if (rc != RT_OK) return rc;
+    // Large frame into a page-locked destination: the kernel stores its finished pixel runs straight into it over PCIe
+    // (the memory is mapped into the device's address space), so the transfer rides along with the rendering instead of
+    // following it.
+    const bool pinned_dst = is_pinned(rgb_out);
+    void *alias = nullptr;
+    const bool zero_copy = pinned_dst && g_zero_copy_min >= 0 && (long long) bytes >= g_zero_copy_min &&
+                           cudaHostGetDevicePointer(&alias, rgb_out, 0) == cudaSuccess && alias;
+    cudaGetLastError();
+    if (!zero_copy) {
+        rc = ensure(&sl.d_frame, &sl.frame_cap, bytes, false);
+        if (rc != RT_OK) return rc;
+    }
     sl.launches = 0;
     CU(cudaEventRecord(sl.ev_start, s->stream));
-    rc = enqueue_part(s, cam, aa, 0, 1, sl.d_frame, kOutFrame, k, s->stream, &sl.launches);
+    rc = enqueue_part(s, cam, aa, 0, 1, zero_copy ? (unsigned char *) alias : sl.d_frame, kOutFrame, k, s->stream, &sl.launches);
     if (rc != RT_OK) return rc;
     CU(cudaEventRecord(sl.ev_kernel, s->stream));
     // while the kernel runs: make sure there is page-locked memory to copy into
-    const bool pinned_dst = is_pinned(rgb_out);
     if (!pinned_dst) {
         rc = ensure(&sl.h_pinned, &sl.pinned_cap, bytes, true);
         if (rc != RT_OK) return rc;
     }
     // the copies go to a second stream so that the next frame's kernel does not queue behind this frame's D2H
     CU(cudaStreamWaitEvent(s->copy_stream, sl.ev_kernel, 0));
-    CU(cudaMemcpyAsync(pinned_dst ? rgb_out : sl.h_pinned, sl.d_frame, bytes, cudaMemcpyDeviceToHost, s->copy_stream));
+    if (!zero_copy) CU(cudaMemcpyAsync(pinned_dst ? rgb_out : sl.h_pinned, sl.d_frame, bytes, cudaMemcpyDeviceToHost, s->copy_stream));
     CU(cudaMemcpyAsync(sl.h_stats, s->buf.control + 8 * k, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->copy_stream));
     CU(cudaEventRecord(sl.ev_done, s->copy_stream));
     sl.busy = true;
