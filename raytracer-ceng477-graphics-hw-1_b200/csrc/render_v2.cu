@@ -41,9 +41,12 @@ constexpr int kMaxP2 = 16;  // kAccShared: item side in pixels when f > 1 (acc s
 #ifndef RT_MIN_CTAS2
 #define RT_MIN_CTAS2 7
 #endif
+#ifndef RT_FORCE_EAGER_LOOP
+#define RT_FORCE_EAGER_LOOP 0  // A/B: run the refill loop (round 1's only shape) even at threshold 0
+#endif
 
 enum Phase : int { kIdle = 0, kClosest = 1, kShadow = 2 };
-enum AccMode : int { kAccShared = 0, kAccRegs = 1 };
+enum AccMode : int { kAccShared = 0, kAccRegs = 1, kAccEager = 2 };
 
 RT_DEV V3 clamp3(V3 c) {  // Vec3f::clamp(0, FLT_MAX), raytracer.cpp:451
     return mk(clamp_ref(c.x, 0.0f, FLT_MAX), clamp_ref(c.y, 0.0f, FLT_MAX), clamp_ref(c.z, 0.0f, FLT_MAX));
@@ -298,6 +301,7 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
 
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
+    (void) lt_mask;
     const int f = p.f, P = p.P;
     const unsigned per_tile = (unsigned) (p.tile_items * p.group_bands), per_group = per_tile * (unsigned) p.tiles_per_group;
     unsigned *work_counter = (unsigned *) p.control;
@@ -408,45 +412,62 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
                 for (int i = lane; i < pw * ph * 3; i += 32) acc[i] = 0u;
                 __syncwarp();
             }
-            int next = 0;        // warp-uniform: next unassigned slot of this item
-            int lx = 0, ly = 0;  // the lane's sub-sample within the item
-            for (;;) {
-                // refill idle lanes with the item's next sub-samples (warp-level work stealing).  Policy: refill only
-                // once at most `refill_threshold` lanes are still busy, so that the rays a warp traces together stay
-                // of one kind and neighbouring (coherent BVH walks, few divergent branches); 31 = refill eagerly,
-                // 0 = only when the whole warp has drained (the default: eager refill measured 17 % slower).
-                const unsigned idle_mask = __ballot_sync(0xffffffffu, L.phase == kIdle);
-                if (idle_mask != 0u && next < total && 32 - __popc(idle_mask) <= p.refill_threshold) {
-                    const int my = next + __popc(idle_mask & lt_mask);
-                    next += __popc(idle_mask);
-                    if (L.phase == kIdle && my < total) {
-                        const int b = my >> 5, l = my & 31;
-                        lx = (b % nbx) * 8 + (l & 7);
-                        ly = (b / nbx) * 4 + (l >> 3);
-                        if (lx < sw && ly < sh) {
-                            start_primary(p, L, E0, Q, U, Vv, px0 * f + lx, py0 * f + ly);
-                            cnt.primary += p.max_depth >= 0;
+            auto sample_done = [&](int lx, int ly, unsigned r8, unsigned g8, unsigned b8) {
+                if (f == 1) {
+                    unsigned char *o = pixel_ptr(p, local_band, ly, px0 + lx, py0 + ly);
+                    o[0] = (unsigned char) r8;
+                    o[1] = (unsigned char) g8;
+                    o[2] = (unsigned char) b8;
+                } else {
+                    RT_CHECK(((ly / f) * pw + (lx / f)) < P * p.Ph);
+                    unsigned *a = &acc[((ly / f) * pw + (lx / f)) * 3];
+                    atomicAdd(a, r8);
+                    atomicAdd(a + 1, g8);
+                    atomicAdd(a + 2, b8);
+                }
+            };
+            if (ACC == kAccShared) {
+                // rounds in lock-step: every lane takes one sub-sample of the next 8x4 block, the warp traces until all of
+                // its paths are finished, then moves on (the measured best: rays of one kind and neighbouring stay together)
+                for (int b = 0; b < nbx * nby; b++) {
+                    const int lx = (b % nbx) * 8 + (lane & 7), ly = (b / nbx) * 4 + (lane >> 3);
+                    if (lx < sw && ly < sh) {
+                        start_primary(p, L, E0, Q, U, Vv, px0 * f + lx, py0 * f + ly);
+                        cnt.primary += p.max_depth >= 0;
+                    }
+                    do {
+                        unsigned r8, g8, b8;
+                        if (trace_step<FAR>(p, L, S, Ia, cnt, r8, g8, b8)) sample_done(lx, ly, r8, g8, b8);
+                    } while (__any_sync(0xffffffffu, L.phase != kIdle));
+                }
+            } else {
+                // kAccEager (experiments, RtBuildOptions.refill_threshold > 0): idle lanes are refilled with the item's next
+                // sub-samples as soon as at most `refill_threshold` lanes are still busy (ballot + popc prefix = warp-level
+                // work stealing; 31 = refill eagerly).  Measured 17 % slower than lock-step rounds on large frames (ray kinds
+                // mix, coherence is lost) and within 1 % on small ones.
+                int next = 0;        // warp-uniform: next unassigned slot of this item
+                int lx = 0, ly = 0;  // the lane's sub-sample within the item
+                for (;;) {
+                    const unsigned idle_mask = __ballot_sync(0xffffffffu, L.phase == kIdle);
+                    if (idle_mask != 0u && next < total && 32 - __popc(idle_mask) <= p.refill_threshold) {
+                        const int my = next + __popc(idle_mask & lt_mask);
+                        next += __popc(idle_mask);
+                        if (L.phase == kIdle && my < total) {
+                            const int b = my >> 5, l = my & 31;
+                            lx = (b % nbx) * 8 + (l & 7);
+                            ly = (b / nbx) * 4 + (l >> 3);
+                            if (lx < sw && ly < sh) {
+                                start_primary(p, L, E0, Q, U, Vv, px0 * f + lx, py0 * f + ly);
+                                cnt.primary += p.max_depth >= 0;
+                            }
                         }
                     }
-                }
-                if (idle_mask == 0xffffffffu && __ballot_sync(0xffffffffu, L.phase != kIdle) == 0u) {
-                    if (next >= total) break;
-                    continue;
-                }
-                unsigned r8, g8, b8;
-                if (trace_step<FAR>(p, L, S, Ia, cnt, r8, g8, b8)) {
-                    if (f == 1) {
-                        unsigned char *o = pixel_ptr(p, local_band, ly, px0 + lx, py0 + ly);
-                        o[0] = (unsigned char) r8;
-                        o[1] = (unsigned char) g8;
-                        o[2] = (unsigned char) b8;
-                    } else {
-                        RT_CHECK(((ly / f) * pw + (lx / f)) < P * p.Ph);
-                        unsigned *a = &acc[((ly / f) * pw + (lx / f)) * 3];
-                        atomicAdd(a, r8);
-                        atomicAdd(a + 1, g8);
-                        atomicAdd(a + 2, b8);
+                    if (idle_mask == 0xffffffffu && __ballot_sync(0xffffffffu, L.phase != kIdle) == 0u) {
+                        if (next >= total) break;
+                        continue;
                     }
+                    unsigned r8, g8, b8;
+                    if (trace_step<FAR>(p, L, S, Ia, cnt, r8, g8, b8)) sample_done(lx, ly, r8, g8, b8);
                 }
             }
             if (f > 1) {  // raytracer.cpp:475-477: truncating integer average of the quantised sub-samples
@@ -487,6 +508,9 @@ int launch_render_v2(const RenderParams &p, int n_ctas, cudaStream_t stream) {
     if (p.acc_mode == kAccRegs) {
         if (p.far_camera) render_kernel_v2<kAccRegs, true><<<n_ctas, kThreads2, 0, stream>>>(p);
         else render_kernel_v2<kAccRegs, false><<<n_ctas, kThreads2, 0, stream>>>(p);
+    } else if (p.refill_threshold > 0 || RT_FORCE_EAGER_LOOP) {
+        if (p.far_camera) render_kernel_v2<kAccEager, true><<<n_ctas, kThreads2, smem, stream>>>(p);
+        else render_kernel_v2<kAccEager, false><<<n_ctas, kThreads2, smem, stream>>>(p);
     } else {
         if (p.far_camera) render_kernel_v2<kAccShared, true><<<n_ctas, kThreads2, smem, stream>>>(p);
         else render_kernel_v2<kAccShared, false><<<n_ctas, kThreads2, smem, stream>>>(p);
