@@ -297,7 +297,8 @@ def cli_walls():
                          "reference_wall_s": r["reference"]["wall_s"] if r.get("reference") else None,
                          "reference_total_s": r["reference"]["total_s"] if r.get("reference") else None,
                          "ppm_identical": r.get("identical")})
-        return rows
+        return {"cuda_startup_probe_s": cli_wall.probe(3), "rows": rows,
+                "note": "ours_wall_s includes the CUDA start-up of a fresh process (cuda_startup_probe_s: `raytracer --probe`)"}
     except Exception as e:  # the CLI binaries are optional for the benchmark
         return {"unavailable": str(e)[:200]}
 

@@ -163,6 +163,11 @@ int main(int argc, char *argv[]) {
             std::string b = argv[++i];
             opt.builder = b == "lbvh" ? RT_BUILD_LBVH_GPU : b == "sah" ? RT_BUILD_SAH_HOST : b == "ploc" ? RT_BUILD_PLOC_GPU : b == "sah_gpu" ? RT_BUILD_SAH_GPU : RT_BUILD_DEFAULT;
         } else if (a == "--stats") opt.want_stats = true;
+        else if (a == "--probe") {
+            // nothing but CUDA start-up (driver, context, kernel load): what a process pays before any of its own work
+            // (tools/cli_wall.py reports it next to the whole-process wall times)
+            return rt_device_count() > 0 && rt_warmup(0) == RT_OK ? 0 : 1;
+        }
         else if (a == "--help" || a == "-h") help = true;
         else xmls.push_back(argv[i]);
     }

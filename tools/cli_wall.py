@@ -72,6 +72,53 @@ def measure(scene, aa, runs, extra=()):
     return res
 
 
+def probe(runs=5):
+    """Wall time of a process that only brings CUDA up (`raytracer --probe`: driver, context, kernel load)."""
+    import harness as H
+    ours = os.path.join(H.PKG, "raytracer")
+    t = []
+    for _ in range(runs):
+        t0 = time.perf_counter()
+        subprocess.run([ours, "--probe"], capture_output=True)
+        t.append(time.perf_counter() - t0)
+    return {"median_s": statistics.median(t), "min_s": min(t), "max_s": max(t)}
+
+
+def batch(aa=1, runs=2):
+    """All shipped scenes: ONE process of this CLI (`raytracer a.xml b.xml ...`: one CUDA start-up) against one process of
+    the reference's binary per scene."""
+    import harness as H
+    scenes = sorted(H.manifest()["scenes"])
+    xmls = [H.golden_scene_path(s) for s in scenes]
+    ours = os.path.join(H.PKG, "raytracer")
+    ref = os.path.join(ROOT, "oracle", "_ref", "raytracer_aa")
+    work = tempfile.mkdtemp(prefix="cliwall_batch_")
+    try:
+        da, db = os.path.join(work, "ours"), os.path.join(work, "ref")
+        os.makedirs(da)
+        os.makedirs(db)
+        t = []
+        for _ in range(runs):
+            t0 = time.perf_counter()
+            p = subprocess.run([ours, *xmls, "--aa", str(aa)], cwd=da, capture_output=True, text=True)
+            t.append(time.perf_counter() - t0)
+            if p.returncode != 0:
+                raise RuntimeError(p.stderr[-400:])
+        own_total = sum(float(x) for x in re.findall(r"Total: ([0-9.]+)", p.stdout))
+        out = {"scenes": len(scenes), "aa": aa, "ours_one_process_wall_s": min(t), "ours_sum_of_totals_s": own_total}
+        if os.path.exists(ref):
+            t0 = time.perf_counter()
+            for x in xmls:
+                subprocess.run([ref, x, "--aa", str(aa)], cwd=db, capture_output=True, check=True)
+            out["reference_processes_wall_s"] = time.perf_counter() - t0
+            names = sorted(os.listdir(db))
+            out["files"] = len(names)
+            out["identical"] = sorted(os.listdir(da)) == names and all(open(os.path.join(da, n), "rb").read() == open(os.path.join(db, n), "rb").read() for n in names)
+        return out
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
 def table(rows, cores):
     out = [f"| scene | AA | cameras | ours: process wall s (median; first run) | ours: Planted / Rendered / Total | reference ({cores} host cores): process wall s | reference: Planted / Rendered / Total | wall speed-up | PPM files |",
            "|---|---|---|---|---|---|---|---|---|"]
@@ -99,10 +146,18 @@ def main():
         scene, _, aa = c.partition(":")
         rows.append(measure(scene, int(aa or 1), a.runs, extra=("--gpus", str(a.gpus)) if a.gpus > 1 else ()))
         print(json.dumps(rows[-1]), flush=True)
+    pr = probe()
     md = table(rows, os.cpu_count())
+    md += (f"\n\nCUDA start-up alone on this box (`raytracer --probe`: driver + context + kernel load, no scene): median {pr['median_s']:.3f} s "
+           f"(min {pr['min_s']:.3f}, max {pr['max_s']:.3f}) — included in every \"ours: process wall\" above.")
+    bt = batch() if a.gpus == 1 else None
+    if bt:
+        md += (f"\n\nAll {bt['scenes']} shipped scenes, no AA ({bt.get('files', '?')} PPM files): ONE process of this CLI {bt['ours_one_process_wall_s']:.3f} s wall "
+               f"(its own \"Total:\" lines add up to {bt['ours_sum_of_totals_s']:.3f} s) against {bt.get('reference_processes_wall_s', float('nan')):.3f} s for the "
+               f"reference's binary run once per scene; files {'byte-identical' if bt.get('identical') else 'DIFFERENT'}.")
     print(md)
     if a.json:
-        json.dump({"host_cores": os.cpu_count(), "rows": rows}, open(a.json, "w"), indent=1)
+        json.dump({"host_cores": os.cpu_count(), "cuda_startup_probe": pr, "batch": bt, "rows": rows}, open(a.json, "w"), indent=1)
     if a.md:
         open(a.md, "w").write(md + "\n")
 
