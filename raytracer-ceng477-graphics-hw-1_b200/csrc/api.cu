@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <numeric>
 #include <string>
 #include <vector>
 
@@ -239,7 +240,7 @@ ItemGeom item_geometry(const RtCamera *cam, int aa, int world) {
         // whole 8x4 blocks of sub-samples: P*f a multiple of 8 and Ph*f a multiple of 4 where the factor allows it
         // (f = 3: 11x11 pixels = 33x33 sub-samples left a fifth block column with one live lane in eight)
         {
-            const int mx = 8 / std::__gcd(8, aa), my = 4 / std::__gcd(4, aa);
+            const int mx = 8 / std::gcd(8, aa), my = 4 / std::gcd(4, aa);
             P = std::max(mx, P / mx * mx);
             Ph = std::max(my, Ph / my * my);
             if (aa > 1 && P > 16) P = 16 / mx * mx > 0 ? 16 / mx * mx : mx;
