@@ -511,7 +511,8 @@ def run_b200(args):
                 "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
                 "e2e": {"value": rays / (e2e_ms_per_step * 1e3), "unit": "Mrays/s", "ms_per_frame": e2e_ms_per_step,
                         "h2d_bytes_per_step": ctypes.sizeof(H.RtCamera) * world, "d2h_bytes_per_step": frame_bytes,
-                        "api": "rt_render (C-ABI) via rt_b200.RayTracer.render into pinned host memory" if world == 1
+                        "api": "rt_render (C-ABI) via rt_b200.RayTracer.render into pinned host memory; for frames >= 32 MB the kernel stores finished "
+                               "pixels straight into that memory over PCIe (no separate D2H copy), timed with the host clock around the call" if world == 1
                         else "rt_render_part_to_host (C-ABI) on every rank: own bands over own PCIe link into a shared page-locked frame, one barrier"},
                 "gpu_launches": args.steps * (world + (1 if (world > 1 and peer is None) else 0)),
                 "scene_build": {"cold_s": build_cold_s, "warm_s": build_warm_s, "device_ms": info.ms_build_device, "host_enqueue_ms": info.ms_build_host,
