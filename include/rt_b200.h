@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 2
+#define RT_B200_ABI_VERSION 3
 
 /* error codes (0 = success, negative = failure; text via rt_last_error()) */
 #define RT_OK 0
@@ -117,6 +117,10 @@ typedef struct RtBuildOptions {
   int32_t force_replay;     /* tests: every ray that reports a hit is re-decided by the exact replay of the reference's
                                traversal (slow; must give the same frame as the default path) */
   int32_t max_ctas_per_sm;  /* experiments: cap on resident CTAs per SM for the render kernel (0 = occupancy limit) */
+  int32_t reinsert_rounds;  /* rounds of insertion-based optimisation of the top-down SAH tree (subtrees move to where the
+                               tree's total box area grows least): 0 = default (8), < 0 = off */
+  float reinsert_accept;    /* the optimised tree is kept when its SAH cost < this x the cost as built (0 = default 0.8;
+                               a large value keeps it always) */
 } RtBuildOptions;
 
 /* counters are exact (device atomics); "ray" = one closest-hit query
@@ -150,6 +154,9 @@ typedef struct RtSceneInfo {
   int32_t device;
   float sah_cost_ploc, sah_cost_sah; /* RT_BUILD_AUTO: the two candidates' SAH costs (computed on the device) */
   float ms_create_wall;  /* wall time of the whole rt_scene_create call */
+  float reinsert_cost_before, reinsert_cost_after; /* SAH cost of the top-down tree as built / after the optimisation rounds */
+  int32_t reinsert_moves, reinsert_rounds;         /* subtrees moved, rounds run (stops early when a round moves nothing) */
+  int32_t reinsert_accepted;                       /* 1: the optimised tree replaced the builder's */
 } RtSceneInfo;
 
 typedef struct RtScene RtScene; /* opaque */
@@ -276,6 +283,10 @@ int rt_device_reference_ranks(const RtSceneDesc *desc, uint32_t *ranks_out, int3
  * in exactly one leaf, every box contains what is below it). Returns the node
  * count (>= 0) or a negative error. */
 int rt_host_check_bvh(const RtSceneDesc *desc, float *sah_cost, int32_t *max_depth);
+/* The plain top-down host tree put through `rounds` rounds of the insertion-based optimisation (the code the GPU build
+ * runs, on the host), then the same invariant check.  cost2 = SAH cost before / after; stats4 = subtrees moved, rounds
+ * run, depth of the resulting tree, 1 if the optimised tree was kept (cost after < accept_ratio x cost before). */
+int rt_host_reinsert(const RtSceneDesc *desc, int rounds, float accept_ratio, float *cost2, int32_t *stats4);
 /* The closed forms the kernels use in place of libm's pow and acos
  * (raytracer.cpp:411-414), compiled for the host. */
 float rt_host_pow_ref(float base, float exponent);

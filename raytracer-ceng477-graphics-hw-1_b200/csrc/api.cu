@@ -21,6 +21,7 @@
 #include "render_params.h"
 #include "rt_b200.h"
 #include "rt_internal.h"
+#include "reinsert_core.h"
 #include "scene_build.h"
 
 namespace rtb {
@@ -425,7 +426,10 @@ int scene_create_impl(const RtSceneDesc *desc, const RtBuildOptions *opts, RtSce
     std::string err;
     const int radius = (opts && opts->ploc_radius > 0) ? opts->ploc_radius : 16;
     const float leaf_cost = (opts && opts->ploc_leaf_cost > 0) ? opts->ploc_leaf_cost : 1.0f;  // tools/ploc_tune.py: 1.0 beats 1.6 and 2.5
-    rc = build.run(*desc, builder, radius, leaf_cost, s->n_sms, s->stream, s->buf, err);
+    // insertion-based optimisation of the top-down tree (reinsert_core.h): on unless switched off
+    const int reinsert_rounds = !opts || opts->reinsert_rounds == 0 ? kReinsertDefaultRounds : (opts->reinsert_rounds < 0 ? 0 : opts->reinsert_rounds);
+    const float reinsert_accept = (opts && opts->reinsert_accept > 0) ? opts->reinsert_accept : kReinsertAccept;
+    rc = build.run(*desc, builder, radius, leaf_cost, reinsert_rounds, reinsert_accept, s->n_sms, s->stream, s->buf, err);
     s->arena = build.arena;
     s->arena_cap = build.arena_bytes;
     build.arena = nullptr;
@@ -499,6 +503,11 @@ int scene_create_impl(const RtSceneDesc *desc, const RtBuildOptions *opts, RtSce
     inf.device = dev;
     inf.sah_cost_ploc = (builder == RT_BUILD_AUTO && np > 1) ? r.sah_cost[0] : 0.0f;
     inf.sah_cost_sah = (builder == RT_BUILD_AUTO && np > 1) ? r.sah_cost[1] : 0.0f;
+    inf.reinsert_cost_before = r.reinsert_cost_before;
+    inf.reinsert_cost_after = r.reinsert_cost_after;
+    inf.reinsert_moves = r.reinsert_moves;
+    inf.reinsert_rounds = r.reinsert_rounds;
+    inf.reinsert_accepted = r.reinsert_accepted;
     inf.ms_create_wall = (float) (now_ms() - t0);
     *out = s;
     return RT_OK;
@@ -713,15 +722,9 @@ int rt_host_reference_ranks(const RtSceneDesc *desc, uint32_t *ranks_out, int32_
 
 // builds the host SAH BVH and checks its invariants: every primitive in exactly one leaf, every child box
 // (after padding) contains the bounds of everything below it.  Returns the node count or a negative error.
-int rt_host_check_bvh(const RtSceneDesc *desc, float *sah_cost, int32_t *max_depth) {
-    int rc = validate(desc);
-    if (rc != RT_OK) return rc;
-    std::vector<Aabb> bounds;
-    primitive_bounds(*desc, bounds);
-    HostBvh bvh;
-    build_bvh_sah_host(bounds, bvh);
-    if (sah_cost) *sah_cost = bvh_sah_cost(bvh);
-    if (max_depth) *max_depth = tree_depth(bvh);
+// invariants of a host tree after the device-side re-layout and padding: every primitive in exactly one leaf and
+// inside its leaf's box, every child box inside its parent's.  Returns the node count or a negative error.
+static int check_host_bvh(HostBvh bvh, const std::vector<Aabb> &bounds) {
     compact_dfs(bvh, 7);  // a depth-first re-layout (here with a breadth-first prefix) must keep the tree intact
     pad_boxes(bvh, bounds);
     const int np = (int) bounds.size();
@@ -741,6 +744,7 @@ int rt_host_check_bvh(const RtSceneDesc *desc, float *sah_cost, int32_t *max_dep
     };
     Aabb all = {{-INFINITY, -INFINITY, -INFINITY}, {INFINITY, INFINITY, INFINITY}};
     st.push_back({0, all});
+    size_t visited = 0;
     while (!st.empty()) {
         Item it = st.back();
         st.pop_back();
@@ -755,16 +759,44 @@ int rt_host_check_bvh(const RtSceneDesc *desc, float *sah_cost, int32_t *max_dep
             }
             continue;
         }
+        if (it.ref >= (int) bvh.nodes.size() || ++visited > bvh.nodes.size()) return fail(RT_ERR_STATE, "node reference out of bounds or a cycle");
         const HostNode &n = bvh.nodes[it.ref];
         for (int c = 0; c < 2; c++) {
             int ch = c ? n.child1 : n.child0;
             if (ch == kEmptyChild) continue;
+            if (!inside(child_box(n, c), it.box)) return fail(RT_ERR_STATE, "child box outside its parent's box");
             st.push_back({ch, child_box(n, c)});
         }
     }
     for (int i = 0; i < np; i++)
         if (seen[i] != 1) return fail(RT_ERR_STATE, "primitive not in exactly one leaf");
     return (int) bvh.nodes.size();
+}
+
+int rt_host_check_bvh(const RtSceneDesc *desc, float *sah_cost, int32_t *max_depth) {
+    int rc = validate(desc);
+    if (rc != RT_OK) return rc;
+    std::vector<Aabb> bounds;
+    primitive_bounds(*desc, bounds);
+    HostBvh bvh;
+    build_bvh_sah_host(bounds, bvh);
+    if (sah_cost) *sah_cost = bvh_sah_cost(bvh);
+    if (max_depth) *max_depth = tree_depth(bvh);
+    return check_host_bvh(bvh, bounds);
+}
+
+int rt_host_reinsert(const RtSceneDesc *desc, int rounds, float accept_ratio, float *cost2, int32_t *stats4) {
+    int rc = validate(desc);
+    if (rc != RT_OK) return rc;
+    std::vector<Aabb> bounds;
+    primitive_bounds(*desc, bounds);
+    HostBvh bvh;
+    build_bvh_sah_host_plain(bounds, bvh);
+    ReinsertReport rep;
+    reinsert_optimize_host(bvh, rounds, accept_ratio, &rep);
+    if (cost2) cost2[0] = rep.cost_before, cost2[1] = rep.accepted ? bvh_sah_cost(bvh) : rep.cost_after;
+    if (stats4) stats4[0] = rep.moves, stats4[1] = rep.rounds, stats4[2] = tree_depth(bvh), stats4[3] = rep.accepted ? 1 : 0;
+    return check_host_bvh(bvh, bounds);
 }
 
 int rt_host_reference_tree_hash(const RtSceneDesc *desc, uint64_t *hash) {

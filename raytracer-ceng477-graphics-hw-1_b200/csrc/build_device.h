@@ -9,6 +9,8 @@
 //   reference tree        level-synchronous midpoint splits + 8 visit-rank arrays                    ref_order_device.cu
 //   candidate trees       Morton sort -> PLOC (cooperative, multi-CTA) or Karras LBVH; top-down binned SAH
 //                                                                                                    bvh_lbvh.cu, bvh_sah_device.cu
+//   reinsertion           the top-down tree optimised by moving subtrees to where the total box area grows least
+//                         (kept when the SAH cost falls below 0.8x)                                  bvh_reinsert.cu
 //   tree_parents/_reduce  per candidate: parent links, then a bottom-up pass (second arrival continues) giving
 //                         every node its inner-node count, height and SAH area sum                   scene_build.cu
 //   choose_kernel         RT_BUILD_AUTO: keeps the PLOC tree when its SAH cost is < 0.8x the top-down tree's
@@ -53,7 +55,9 @@ struct BuildResult {
     int ref_overflow;    // reference tree deeper than the replay stack (cannot happen: depth cap 19)
     unsigned scene_bounds[6];     // ordered-uint min xyz, max xyz over all primitive bounds
     unsigned centroid_bounds[6];  // the same over box centres (Morton quantisation)
-    int pad[6];
+    float reinsert_cost_before, reinsert_cost_after;  // bvh_reinsert.cu: SAH cost of the top-down tree as built / optimised
+    int reinsert_moves, reinsert_rounds, reinsert_accepted;
+    int pad[1];
 };
 static_assert(sizeof(BuildResult) == 128, "BuildResult is copied back as one 128-byte block");
 
@@ -151,5 +155,23 @@ struct SahScratch {
 constexpr int kSahLevels = 64;
 int sah_max_grid(int n_sms);
 int enqueue_sah(const Aabb *bounds, int n, const SahScratch &s, DevTree &out, const BuildResult *res, int grid, cudaStream_t stream);
+
+// ---- insertion-based optimisation of a finished tree (bvh_reinsert.cu, reinsert_core.h) ----------------------------
+struct ReinsertScratch {
+    Aabb *box;                       // [ne] entity arrays: inner node i = entity i, leaf range starting at f = t.cap + f
+    int *left, *right, *parent;      // [ne]
+    unsigned long long *lock, *key;  // [ne]
+    int *mv_y, *mv_pivot;            // [ne]
+    float *partial;                  // [grid] per-CTA partial sums
+    int *counters;                   // [reinsert_counter_slots()]
+    int ne;
+};
+int reinsert_max_grid(int n_sms);
+int reinsert_counter_slots();
+// `rounds` rounds on the tree `t` (all node slots reachable, no missing child — the top-down SAH builder's output);
+// the optimised tree replaces t's nodes when its SAH cost < accept_ratio x the cost before and it is not deeper than
+// the traversal stack; res->reinsert_* report.  Returns a cudaError_t as int.
+int enqueue_reinsert(const DevTree &t, const ReinsertScratch &s, int rounds, float accept_ratio, BuildResult *res, int grid,
+                     cudaStream_t stream);
 
 }  // namespace rtb

@@ -8,6 +8,7 @@
 #include <cfloat>
 #include <cmath>
 
+#include "reinsert_core.h"
 #include "rt_internal.h"
 
 namespace rtb {
@@ -126,7 +127,7 @@ struct SahBuilder {
 
 }  // namespace
 
-void build_bvh_sah_host(const std::vector<Aabb> &bounds, HostBvh &out) {
+void build_bvh_sah_host_plain(const std::vector<Aabb> &bounds, HostBvh &out) {
     out = HostBvh();
     const int np = (int) bounds.size();
     if (np == 0) return;
@@ -148,6 +149,113 @@ void build_bvh_sah_host(const std::vector<Aabb> &bounds, HostBvh &out) {
     }
     out.prim_order = b.ids;
     out.sah_cost = bvh_sah_cost(out);
+}
+
+// Insertion-based optimisation of a finished host tree: the rounds of reinsert_core.h run one after the other, every
+// round exactly as the GPU kernel runs it (all searches on the unchanged tree, locks by largest key, winners applied),
+// so the host and the device produce the same tree from the same input.  Returns the number of applied moves; the
+// tree is only replaced when the optimised SAH cost is below accept_ratio x the cost it came with and the result
+// fits the traversal stack.
+int reinsert_optimize_host(HostBvh &bvh, int rounds, float accept_ratio, ReinsertReport *report) {
+    ReinsertReport rep;
+    const int cap = (int) bvh.nodes.size(), np = (int) bvh.prim_order.size();
+    rep.cost_before = rep.cost_after = bvh.sah_cost;
+    if (report) *report = rep;
+    if (cap < 3 || rounds <= 0) return 0;
+    for (auto &n: bvh.nodes)
+        if (n.child0 == kEmptyChild || n.child1 == kEmptyChild) return 0;
+    const int ne = cap + np + 1;
+    if (ne >= kReinsertMaxEntities) return 0;
+    if (rounds > kReinsertMaxRounds) rounds = kReinsertMaxRounds;
+    std::vector<Aabb> box(ne);
+    std::vector<int> left(ne, -1), right(ne, -1), parent(ne, -1);
+    for (int i = 0; i < cap; i++) {
+        const HostNode &n = bvh.nodes[i];
+        const int ch[2] = {n.child0, n.child1};
+        const float *mns[2] = {n.c0mn, n.c1mn}, *mxs[2] = {n.c0mx, n.c1mx};
+        int ce[2];
+        for (int c = 0; c < 2; c++) {
+            ce[c] = ch[c] >= 0 ? ch[c] : cap + ((~ch[c]) >> 3);
+            if (ch[c] < 0) left[ce[c]] = ch[c];
+            for (int k = 0; k < 3; k++) box[ce[c]].mn[k] = mns[c][k], box[ce[c]].mx[k] = mxs[c][k];
+            parent[ce[c]] = i;
+        }
+        left[i] = ce[0], right[i] = ce[1];
+    }
+    box[0] = box_merge(box[left[0]], box[right[0]]);
+    ReinsertView t{box.data(), left.data(), right.data(), parent.data()};
+    auto cost = [&]() {
+        double c = 0;
+        std::vector<int> todo(1, 0);
+        while (!todo.empty()) {
+            const int e = todo.back();
+            todo.pop_back();
+            c += reinsert_node_cost(t, e, kCostNode, kCostPrim);
+            if (left[left[e]] >= 0) todo.push_back(left[e]);
+            if (left[right[e]] >= 0) todo.push_back(right[e]);
+        }
+        const float ra = box_half_area(box[0]);
+        return ra > 0 ? (float) (kCostNode + c / ra) : 0.0f;
+    };
+    rep.cost_before = cost();
+    const float min_gain = 1e-6f * box_half_area(box[0]);
+    std::vector<unsigned long long> lock(ne, 0ull), key(ne);
+    std::vector<ReinsertMove> mv(ne);
+    std::vector<char> has(ne);
+    for (int round = 0; round < rounds; round++) {
+        for (int x = 0; x < ne; x++) {
+            has[x] = (x == 0 || parent[x] >= 0) && reinsert_find(t, x, min_gain, mv[x]);
+            if (!has[x]) continue;
+            key[x] = reinsert_key(round, mv[x].gain, x);
+            if (!reinsert_paths(t, x, mv[x].y, mv[x].pivot, [&](int n) { lock[n] = std::max(lock[n], key[x]); return true; })) has[x] = 0;
+        }
+        for (int x = 0; x < ne; x++)
+            if (has[x] && !reinsert_paths(t, x, mv[x].y, mv[x].pivot, [&](int n) { return lock[n] == key[x]; })) has[x] = 0;
+        int applied = 0;
+        for (int x = 0; x < ne; x++)
+            if (has[x]) reinsert_apply(t, x, mv[x].y, mv[x].pivot), applied++;
+        rep.moves += applied;
+        rep.rounds = round + 1;
+        if (applied == 0) break;
+    }
+    rep.cost_after = cost();
+    // height of the optimised tree (a node over two leaves: 1)
+    int height = 0;
+    {
+        std::vector<std::pair<int, int>> todo(1, {0, 1});
+        while (!todo.empty()) {
+            auto [e, d] = todo.back();
+            todo.pop_back();
+            height = std::max(height, d);
+            if (left[left[e]] >= 0) todo.emplace_back(left[e], d + 1);
+            if (left[right[e]] >= 0) todo.emplace_back(right[e], d + 1);
+        }
+    }
+    rep.height = height;
+    rep.accepted = rep.cost_after < accept_ratio * rep.cost_before && height <= 60;
+    if (rep.accepted) {
+        for (int i = 0; i < cap; i++) {
+            HostNode &n = bvh.nodes[i];
+            const int ce[2] = {left[i], right[i]};
+            for (int k = 0; k < 3; k++) {
+                n.c0mn[k] = box[ce[0]].mn[k], n.c0mx[k] = box[ce[0]].mx[k];
+                n.c1mn[k] = box[ce[1]].mn[k], n.c1mx[k] = box[ce[1]].mx[k];
+            }
+            n.child0 = ce[0] < cap ? ce[0] : left[ce[0]];
+            n.child1 = ce[1] < cap ? ce[1] : left[ce[1]];
+        }
+        bvh.max_depth = height;
+        bvh.sah_cost = bvh_sah_cost(bvh);
+    }
+    if (report) *report = rep;
+    return rep.accepted ? rep.moves : 0;
+}
+
+void build_bvh_sah_host(const std::vector<Aabb> &bounds, HostBvh &out, int reinsert_rounds, float reinsert_accept) {
+    build_bvh_sah_host_plain(bounds, out);
+    if (reinsert_rounds < 0) reinsert_rounds = kReinsertDefaultRounds;
+    if (!(reinsert_accept > 0)) reinsert_accept = kReinsertAccept;
+    reinsert_optimize_host(out, reinsert_rounds, reinsert_accept);
 }
 
 // Padding: per axis  1e-4 * extent  +  4e-6 * (scene diagonal + largest |coordinate| of the box).

@@ -97,7 +97,19 @@ void build_reference_ranks(const RtSceneDesc &d, std::vector<uint32_t> &ranks /*
                            RefTree *tree = nullptr);
 
 // Host binned-SAH BVH2 (quality yardstick and fallback for tiny scenes).
-void build_bvh_sah_host(const std::vector<Aabb> &bounds, HostBvh &out);
+// build_bvh_sah_host = the plain top-down build followed by reinsert_optimize_host with the library's defaults
+// (kReinsertDefaultRounds rounds, kept when the SAH cost falls below kReinsertAccept x the plain tree's).
+void build_bvh_sah_host_plain(const std::vector<Aabb> &bounds, HostBvh &out);
+void build_bvh_sah_host(const std::vector<Aabb> &bounds, HostBvh &out, int reinsert_rounds = -1, float reinsert_accept = 0.0f);
+
+// Insertion-based optimisation (reinsert_core.h) of a finished tree, on the host; the GPU pipeline runs the same rounds
+// in bvh_reinsert.cu.
+struct ReinsertReport {
+    float cost_before = 0, cost_after = 0;  // SAH cost of the tree as built / after the rounds
+    int moves = 0, rounds = 0, height = 0;
+    bool accepted = false;
+};
+int reinsert_optimize_host(HostBvh &bvh, int rounds, float accept_ratio, ReinsertReport *report = nullptr);
 
 // Outward padding applied to every child box before upload (conservative node test; the
 // primitive tests stay exact).  See DESIGN.md "why the boxes are padded".

@@ -370,6 +370,7 @@ struct Scratch {
     PlocScratch ploc;
     LbvhScratch lbvh;
     SahScratch sah;
+    ReinsertScratch reinsert;
     DevTree tree[2];
 };
 
@@ -386,7 +387,7 @@ void carve_tree(Bump &b, DevTree &t, int cap, int np) {
     t.area = b.take<float>(cap);
 }
 
-void carve_scratch(Bump &b, Scratch &s, const RtSceneDesc &d, int builder, int ploc_grid) {
+void carve_scratch(Bump &b, Scratch &s, const RtSceneDesc &d, int builder, int ploc_grid, int reinsert_grid) {
     const int nt = d.n_triangles, ns = d.n_spheres, np = nt + ns;
     s.vertices = b.take<RtVec3>(d.n_vertices);
     s.triangles = b.take<RtTriangle>(nt);
@@ -435,6 +436,20 @@ void carve_scratch(Bump &b, Scratch &s, const RtSceneDesc &d, int builder, int p
         s.sah.root_ref = b.take<int>(1);
         s.sah.cap_tasks = cap;
         s.sah.cap_nodes = cap + 1;
+    }
+    if (sah && reinsert_grid > 0) {
+        const size_t ne = (size_t) (cap + 1) + cap + 1;  // node slots + leaf ranges by first primitive
+        s.reinsert.ne = (int) ne;
+        s.reinsert.box = b.take<Aabb>(ne);
+        s.reinsert.left = b.take<int>(ne);
+        s.reinsert.right = b.take<int>(ne);
+        s.reinsert.parent = b.take<int>(ne);
+        s.reinsert.lock = b.take<unsigned long long>(ne);
+        s.reinsert.key = b.take<unsigned long long>(ne);
+        s.reinsert.mv_y = b.take<int>(ne);
+        s.reinsert.mv_pivot = b.take<int>(ne);
+        s.reinsert.partial = b.take<float>(reinsert_grid);
+        s.reinsert.counters = b.take<int>(reinsert_counter_slots());
     }
     carve_tree(b, s.tree[0], cap + 1, cap);
     if (builder == RT_BUILD_AUTO) carve_tree(b, s.tree[1], cap + 1, cap);
@@ -575,21 +590,24 @@ void SceneBuild::release_scratch() {
     scratch = nullptr;
 }
 
-int SceneBuild::run(const RtSceneDesc &d, int builder, int ploc_radius, float ploc_leaf_cost, int n_sms, cudaStream_t stream,
-                    SceneBuffers &out, std::string &err) {
+int SceneBuild::run(const RtSceneDesc &d, int builder, int ploc_radius, float ploc_leaf_cost, int reinsert_rounds, float reinsert_accept,
+                    int n_sms, cudaStream_t stream, SceneBuffers &out, std::string &err) {
     const int nt = d.n_triangles, ns = d.n_spheres, np = nt + ns;
     const double t_begin = now_ms();
     int ploc_grid = 1;
     if (builder == RT_BUILD_AUTO || builder == RT_BUILD_PLOC_GPU) ploc_grid = ploc_max_grid(n_sms);
     last_builder = builder;
     last_ploc_grid = ploc_grid;
+    const bool sah_device = builder == RT_BUILD_AUTO || builder == RT_BUILD_SAH_GPU;
+    const int reinsert_grid = (sah_device && reinsert_rounds > 0 && np > 2) ? reinsert_max_grid(n_sms) : 0;
+    last_reinsert_grid = reinsert_grid;
 
     // ---- the two arenas -----------------------------------------------------------------------------------
     Bump size_scene, size_scratch;
     SceneBuffers dummy_o;
     Scratch dummy_s = Scratch();
     carve_scene(size_scene, dummy_o, d);
-    carve_scratch(size_scratch, dummy_s, d, builder, ploc_grid);
+    carve_scratch(size_scratch, dummy_s, d, builder, ploc_grid, reinsert_grid);
     arena = block_acquire(size_scene.off + 256, &arena_bytes);
     scratch = block_acquire(size_scratch.off + 256, &scratch_bytes);
     if (!arena || !scratch) {
@@ -601,7 +619,7 @@ int SceneBuild::run(const RtSceneDesc &d, int builder, int ploc_radius, float pl
     bx.base = (char *) scratch;
     Scratch s = Scratch();
     carve_scene(bs, out, d);
-    carve_scratch(bx, s, d, builder, ploc_grid);
+    carve_scratch(bx, s, d, builder, ploc_grid, reinsert_grid);
 
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     CKB(cudaEventCreate(&e0));
@@ -686,6 +704,13 @@ int SceneBuild::run(const RtSceneDesc &d, int builder, int ploc_radius, float pl
                     err = std::string("SAH builder launch: ") + cudaGetErrorString((cudaError_t) e);
                     return -1;
                 }
+                if (reinsert_grid > 0) {
+                    const int e2 = enqueue_reinsert(t, s.reinsert, reinsert_rounds, reinsert_accept, out.result, reinsert_grid, stream);
+                    if (e2 != 0) {
+                        err = std::string("reinsertion launch: ") + cudaGetErrorString((cudaError_t) e2);
+                        return -1;
+                    }
+                }
                 n_candidates = builder == RT_BUILD_AUTO ? 2 : 1;
             }
         }
@@ -722,7 +747,7 @@ int SceneBuild::run(const RtSceneDesc &d, int builder, int ploc_radius, float pl
         std::vector<Aabb> hb;
         primitive_bounds(d, hb);
         HostBvh bvh;
-        build_bvh_sah_host(hb, bvh);
+        build_bvh_sah_host(hb, bvh, reinsert_rounds, reinsert_accept);
         if ((int) bvh.nodes.size() > s.tree[0].cap) {
             err = "host BVH larger than the node arena";
             return -1;
@@ -766,7 +791,7 @@ int SceneBuild::read_reference_tree(const RtSceneDesc &d, cudaStream_t stream, c
     Bump bx;
     bx.base = (char *) scratch;
     Scratch s = Scratch();
-    carve_scratch(bx, s, d, last_builder, last_ploc_grid);
+    carve_scratch(bx, s, d, last_builder, last_ploc_grid, last_reinsert_grid);
     const int n_nodes = result.ref_nodes;
     std::vector<DevRefNode> dn((size_t) n_nodes);
     CKB(cudaMemcpyAsync(dn.data(), s.ref.nodes, sizeof(DevRefNode) * n_nodes, cudaMemcpyDeviceToHost, stream));

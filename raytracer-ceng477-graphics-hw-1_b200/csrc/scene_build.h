@@ -42,11 +42,13 @@ struct SceneBuild {
     float ms_device = 0;            // CUDA events around uploads + every build kernel
     float ms_host_before_sync = 0;  // host time until everything was enqueued
     float ms_wall = 0;
-    int last_builder = 0, last_ploc_grid = 1;
+    int last_builder = 0, last_ploc_grid = 1, last_reinsert_grid = 0;
 
     // Enqueues and completes the whole build on `stream`.  0 on success; < 0 with `err` set.
-    int run(const RtSceneDesc &d, int builder, int ploc_radius, float ploc_leaf_cost, int n_sms, cudaStream_t stream,
-            SceneBuffers &out, std::string &err);
+    // reinsert_rounds: rounds of insertion-based optimisation on the top-down tree (0 = none); reinsert_accept: the
+    // optimised tree is kept when its SAH cost < reinsert_accept x the builder's
+    int run(const RtSceneDesc &d, int builder, int ploc_radius, float ploc_leaf_cost, int reinsert_rounds, float reinsert_accept,
+            int n_sms, cudaStream_t stream, SceneBuffers &out, std::string &err);
     // test hook: the reference-order tree as ref_order.cpp numbers it, read back from the scratch arena
     int read_reference_tree(const RtSceneDesc &d, cudaStream_t stream, const SceneBuffers &out, std::vector<uint32_t> &ranks,
                             RefTreeStats &stats, RefTree &tree, std::string &err);

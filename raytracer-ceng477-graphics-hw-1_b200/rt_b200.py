@@ -64,7 +64,8 @@ class RtCamera(C.Structure):
 class RtBuildOptions(C.Structure):
     _fields_ = [("builder", C.c_int32), ("brute_force", C.c_int32), ("no_exact_culling", C.c_int32),
                 ("refill_threshold", C.c_int32), ("ploc_radius", C.c_int32), ("ploc_leaf_cost", C.c_float),
-                ("force_replay", C.c_int32), ("max_ctas_per_sm", C.c_int32)]
+                ("force_replay", C.c_int32), ("max_ctas_per_sm", C.c_int32),
+                ("reinsert_rounds", C.c_int32), ("reinsert_accept", C.c_float)]
 
 
 class RtStats(C.Structure):
@@ -84,7 +85,8 @@ class RtSceneInfo(C.Structure):
                 ("ref_tree_max_leaf", C.c_int32), ("ref_tree_max_depth", C.c_int32),
                 ("ms_build_host", C.c_float), ("ms_build_device", C.c_float), ("bvh_sah_cost", C.c_float),
                 ("builder", C.c_int32), ("device", C.c_int32), ("sah_cost_ploc", C.c_float), ("sah_cost_sah", C.c_float),
-                ("ms_create_wall", C.c_float)]
+                ("ms_create_wall", C.c_float), ("reinsert_cost_before", C.c_float), ("reinsert_cost_after", C.c_float),
+                ("reinsert_moves", C.c_int32), ("reinsert_rounds", C.c_int32), ("reinsert_accepted", C.c_int32)]
 
 
 class Scene:
@@ -283,11 +285,11 @@ class RayTracer:
     """RayTracer(scene) / render(camera) — raytracer.cpp:335, :362 — on the current CUDA device."""
 
     def __init__(self, scene, builder=RT_BUILD_DEFAULT, brute_force=False, exact_culling=True, refill_threshold=0,
-                 ploc_radius=0, ploc_leaf_cost=0.0, force_replay=False, max_ctas_per_sm=0):
+                 ploc_radius=0, ploc_leaf_cost=0.0, force_replay=False, max_ctas_per_sm=0, reinsert_rounds=0, reinsert_accept=0.0):
         self.L = cuda_lib()
         self.scene = scene
         opts = RtBuildOptions(builder, 1 if brute_force else 0, 0 if exact_culling else 1, refill_threshold, ploc_radius, ploc_leaf_cost,
-                              1 if force_replay else 0, max_ctas_per_sm)
+                              1 if force_replay else 0, max_ctas_per_sm, reinsert_rounds, reinsert_accept)
         h = C.c_void_p()
         _check(self.L.rt_scene_create(C.byref(scene.desc), C.byref(opts), C.byref(h)))
         self.h = h

@@ -21,7 +21,7 @@ def test_every_declared_symbol_is_exported():
     assert len(names) >= 15
     for n in names:
         assert hasattr(L, n), n
-    assert L.rt_abi_version() == 2
+    assert L.rt_abi_version() == 3
 
 
 def test_band_partition_arithmetic():

@@ -4,6 +4,8 @@ frames rendered by the unmodified reference, and against the oracle on seeded/ad
 Tolerance (BASELINE.json north_star): |delta| <= 1 per 8-bit channel on >= 99.9 % of pixels and zero pixels off by
 more than 8.  The design goal is stricter — byte identity — and each test prints the exact counts.
 """
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -159,19 +161,46 @@ def test_oracle_on_odd_configuration():
 
 @pytest.mark.parametrize("key", ["simple.aa1", "cornellbox_front.aa1", "marbles.aa1", "bunny.aa1", "horse_and_mug.aa1",
                                  "dragon_lowres.aa1", "low_poly_scene.aa1", "mirror_spheres.aa1", "Car.aa1"])
-@pytest.mark.parametrize("builder", ["lbvh", "ploc", "sah_gpu"])
+@pytest.mark.parametrize("builder", ["lbvh", "ploc", "sah_gpu", "sah_gpu_plain", "sah_gpu_reinserted"])
 def test_gpu_bvh_builders(key, builder):
     """The BVHs built on the GPU (Morton + bitonic sort, then Karras' radix tree or PLOC clustering, SAH leaf collapse)
     must give the same frames: the tree is only a filter, ties are settled by the reference-order ranks."""
     gold, m = H.golden_image(key)
     sc = H.golden_scene(m["scene"])
-    rt = tracer(m["scene"], builder={"lbvh": H.rt_b200.RT_BUILD_LBVH_GPU, "ploc": H.rt_b200.RT_BUILD_PLOC_GPU, "sah_gpu": H.rt_b200.RT_BUILD_SAH_GPU}[builder])
+    # sah_gpu_plain: the top-down tree as built; sah_gpu_reinserted: 16 rounds of the insertion-based optimisation, kept
+    # whatever they produce; sah_gpu: the default (8 rounds, kept when the SAH cost falls below 0.8x)
+    kw = {"sah_gpu_plain": {"reinsert_rounds": -1}, "sah_gpu_reinserted": {"reinsert_rounds": 16, "reinsert_accept": 1e9}}.get(builder, {})
+    rt = tracer(m["scene"], builder={"lbvh": H.rt_b200.RT_BUILD_LBVH_GPU, "ploc": H.rt_b200.RT_BUILD_PLOC_GPU}.get(builder, H.rt_b200.RT_BUILD_SAH_GPU), **kw)
     img = rt.render(sc.camera(m["camera"]), 1)
+    if builder.startswith("sah_gpu"):
+        i = rt.info()
+        print(f"   reinsertion: {i.reinsert_moves} moves in {i.reinsert_rounds} rounds, SAH {i.reinsert_cost_before:.3f} -> {i.reinsert_cost_after:.3f}, kept {i.reinsert_accepted}")
+        assert i.reinsert_accepted == (1 if builder == "sah_gpu_reinserted" and i.reinsert_moves > 0 else i.reinsert_accepted)
+        assert builder != "sah_gpu_plain" or (i.reinsert_moves == 0 and i.reinsert_accepted == 0)
     inf, ref_inf = rt.info(), tracer(m["scene"], builder=H.rt_b200.RT_BUILD_SAH_HOST).info()
     print(key, H.diff_report(gold, img), f"{builder}: {inf.bvh_nodes} nodes depth {inf.bvh_max_depth} sah {inf.bvh_sah_cost:.1f} "
           f"build {inf.ms_build_device:.3f} ms device, {rt.last_stats.ms_render:.3f} ms render | sah_host: {ref_inf.bvh_nodes} nodes "
           f"sah {ref_inf.bvh_sah_cost:.1f} build {ref_inf.ms_build_host:.1f} ms host")
     assert np.array_equal(img, gold)
+
+
+@pytest.mark.parametrize("scene", ["cornellbox", "marbles", "bunny", "horse_and_mug", "car", "dragon_lowres"])
+def test_reinsertion_on_gpu_equals_host(scene):
+    """bvh_reinsert.cu against reinsert_core.h run on the host (rt_host_reinsert): the top-down trees are the same on
+    both sides and so are the rounds — the same number of subtrees move, the same SAH cost comes out."""
+    L = H.rt_b200.cuda_lib()
+    L.rt_host_reinsert.argtypes = [C.POINTER(H.RtSceneDesc), C.c_int, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
+    sc = H.golden_scene(scene)
+    cost, stats = (C.c_float * 2)(), (C.c_int32 * 4)()
+    assert L.rt_host_reinsert(C.byref(sc.desc), 8, 1e9, cost, stats) >= 1, L.rt_last_error()
+    rt = H.RayTracer(sc, builder=H.rt_b200.RT_BUILD_SAH_GPU, reinsert_rounds=8, reinsert_accept=1e9)
+    i = rt.info()
+    rt.close()
+    print(scene, "host", list(cost), list(stats), "device", i.reinsert_cost_before, i.reinsert_cost_after, i.reinsert_moves, i.reinsert_rounds,
+          "depth", i.bvh_max_depth, f"build {i.ms_build_device:.3f} ms")
+    assert i.reinsert_moves == stats[0] and i.reinsert_rounds == stats[1] and i.bvh_max_depth == stats[2]
+    assert i.reinsert_cost_before == pytest.approx(cost[0], rel=1e-4) and i.reinsert_cost_after == pytest.approx(cost[1], rel=1e-4)
+    assert i.bvh_sah_cost == pytest.approx(cost[1], rel=1e-4)
 
 
 @pytest.mark.slow

@@ -153,6 +153,46 @@ def test_host_bvh_invariants(scene):
     assert 0 < depth.value <= 60 and cost.value > 0
 
 
+def _host_reinsert(scene, rounds, accept):
+    L = H.rt_b200.cuda_lib()
+    L.rt_host_reinsert.argtypes = [C.POINTER(H.RtSceneDesc), C.c_int, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
+    sc = H.golden_scene(scene)
+    cost, stats = (C.c_float * 2)(), (C.c_int32 * 4)()
+    n = L.rt_host_reinsert(C.byref(sc.desc), rounds, accept, cost, stats)
+    assert n >= 1, L.rt_last_error()  # every primitive still in exactly one leaf, every box inside its parent's
+    return n, list(cost), list(stats)
+
+
+@pytest.mark.parametrize("scene", ["cornellbox", "marbles", "bunny", "horse_and_mug", "low_poly", "car", "mirror_spheres"])
+def test_reinsertion_keeps_the_tree_valid_and_never_raises_its_cost(scene):
+    """reinsert_core.h (the code the GPU build runs, here on the host): subtrees move, the tree stays a valid BVH over
+    the same leaves, its SAH cost does not rise, and more rounds are never worse than fewer."""
+    n0, c0, s0 = _host_reinsert(scene, 0, 1e9)
+    n8, c8, s8 = _host_reinsert(scene, 8, 1e9)  # accept whatever the rounds produce
+    n16, c16, s16 = _host_reinsert(scene, 16, 1e9)
+    print(scene, "cost", c0, c8, c16, "moves/rounds/depth/kept", s0, s8, s16)
+    assert n0 == n8 == n16  # nodes are re-used, never added or dropped
+    assert s0[0] == 0 and c0[1] == pytest.approx(c0[0], rel=1e-6)
+    assert c8[1] <= c8[0] * (1 + 1e-6) and c16[1] <= c8[1] * (1 + 1e-5)
+    assert s8[2] <= 60 and s16[2] <= 60
+
+
+def test_reinsertion_repairs_the_floor_of_horse_and_mug():
+    """The case it exists for (tools/tree_lab.cpp): the top-down builder carries the two floor triangles deep into the
+    hierarchy (SAH cost 7.19); eight rounds move them to the root (4.38, below PLOC's 4.44) — node steps per ray on the
+    renderer's own rays fall from 8.6 to 5.8."""
+    _, cost, stats = _host_reinsert("horse_and_mug", 8, 0.8)
+    assert stats[3] == 1 and stats[0] > 100
+    assert 7.0 < cost[0] < 7.4 and 4.3 < cost[1] < 4.45
+
+
+def test_reinsertion_is_not_kept_where_it_does_not_clearly_pay():
+    """The default acceptance (SAH cost below 0.8x): car drops from 3.58 to 3.12 only, the rays get slower (secondary rays
+    start on surfaces; tools/tree_lab.cpp) — the builder's tree stays."""
+    _, cost, stats = _host_reinsert("car", 8, 0.8)
+    assert stats[3] == 0 and stats[0] == 0 or cost[1] >= 0.8 * cost[0]
+
+
 def test_prolog_before_root_is_accepted(tmp_path):
     """parser.cpp:17 takes the document's FIRST CHILD as the root, so the reference dereferences NULL on a file that
     starts with an XML declaration or a comment (none of its 13 inputs does).  The product's loader skips

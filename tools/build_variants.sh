@@ -6,7 +6,7 @@ set -e
 HERE="$(cd "$(dirname "$0")/.." && pwd)"
 PKG="$HERE/raytracer-ceng477-graphics-hw-1_b200"
 mkdir -p "$PKG/ab"
-SRCS="$PKG/csrc/render_v2.cu $PKG/csrc/assemble.cu $PKG/csrc/api.cu $PKG/csrc/scene_build.cu $PKG/csrc/bvh_lbvh.cu $PKG/csrc/bvh_sah_device.cu $PKG/csrc/ref_order_device.cu $PKG/csrc/selftest.cu $PKG/csrc/ref_order.cpp $PKG/csrc/bvh_host.cpp"
+SRCS="$PKG/csrc/render_v2.cu $PKG/csrc/assemble.cu $PKG/csrc/api.cu $PKG/csrc/scene_build.cu $PKG/csrc/bvh_lbvh.cu $PKG/csrc/bvh_sah_device.cu $PKG/csrc/bvh_reinsert.cu $PKG/csrc/ref_order_device.cu $PKG/csrc/selftest.cu $PKG/csrc/ref_order.cpp $PKG/csrc/bvh_host.cpp"
 for v in "$@"; do
   name="${v%%:*}"; flags="${v#*:}"
   [ "$flags" = "$v" ] && flags=""
