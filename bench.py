@@ -516,7 +516,9 @@ def run_b200(args):
                         else "rt_render_part_to_host (C-ABI) on every rank: own bands over own PCIe link into a shared page-locked frame, one barrier"},
                 "gpu_launches": args.steps * (world + (1 if (world > 1 and peer is None) else 0)),
                 "scene_build": {"cold_s": build_cold_s, "warm_s": build_warm_s, "device_ms": info.ms_build_device, "host_enqueue_ms": info.ms_build_host,
-                                "sah_cost_ploc": info.sah_cost_ploc, "sah_cost_sah": info.sah_cost_sah,
+                                "sah_cost_ploc": info.sah_cost_ploc, "sah_cost_sah": info.sah_cost_sah, "sah_cost_kept": info.bvh_sah_cost,
+                                "reinsertion": {"moves": info.reinsert_moves, "rounds": info.reinsert_rounds, "sah_cost_before": info.reinsert_cost_before,
+                                                "sah_cost_after": info.reinsert_cost_after, "kept": bool(info.reinsert_accepted)},
                                 "note": "cold = first rt_scene_create of the process (loads the library's kernels); warm = median of 3 more",
                                 "dynamic_scene_ms_per_frame": build_warm_s * 1e3 + e2e_ms_per_step},
                 "roofline": roofline}

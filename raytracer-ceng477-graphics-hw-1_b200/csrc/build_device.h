@@ -162,6 +162,7 @@ struct ReinsertScratch {
     int *left, *right, *parent;      // [ne]
     unsigned long long *lock, *key;  // [ne]
     int *mv_y, *mv_pivot;            // [ne]
+    int *canon;                      // [ne] run-independent id of an entity: depth-first index of the tree as built
     float *partial;                  // [grid] per-CTA partial sums
     int *counters;                   // [reinsert_counter_slots()]
     int ne;

@@ -5,6 +5,11 @@
 // nodes when it is worth it (SAH cost below accept_ratio x the builder's, not deeper than the traversal stack).
 // Nothing leaves the device; the host learns what happened from five fields of the BuildResult block.
 //
+// Determinism: the builder hands out node slots with an atomic counter, so slot numbers differ from run to run.  Locks
+// are therefore keyed by a node's position in the depth-first order of the tree as built (computed here, once) — the
+// numbering the host builder produces by construction — and never by its slot: equal gains resolve the same way in
+// every run and exactly as in reinsert_optimize_host (tests compare the two).
+//
 // Input requirements (met by the top-down SAH builder, bvh_sah_device.cu): every node slot below *n_used is reachable
 // from node 0, and no child is missing.  A tree that breaks them is left untouched.
 #include <cfloat>
@@ -95,6 +100,45 @@ __global__ void __launch_bounds__(kRT) reinsert_kernel(DevTree t, ReinsertScratc
     grid.sync();
     if (__ldcg(&s.counters[kBad]) != 0) return;  // uniform
 
+    // ---- canonical ids: depth-first (pre-order) index of every inner node, leaves keep cap + first primitive --------
+    // inner nodes below each node, bottom-up: whoever completes a node (second arrival) carries on to its parent
+    // (mv_y = arrivals, mv_pivot = subtree size: both are free until the first round)
+    for (int i = tid; i < n_used; i += nthreads) s.mv_y[i] = 0;
+    grid.sync();
+    for (int i = tid; i < n_used; i += nthreads) {
+        const int leaf_children = (s.left[s.left[i]] < 0 ? 1 : 0) + (s.left[s.right[i]] < 0 ? 1 : 0);
+        if (leaf_children == 0) continue;
+        if (leaf_children == 1 && atomicAdd(&s.mv_y[i], 1) != 1) continue;
+        int cur = i;
+        for (int guard = 0; guard < (1 << 24); guard++) {
+            __threadfence();
+            const int l = s.left[cur], r = s.right[cur];
+            int count = 1;
+            if (s.left[l] >= 0) count += __ldcg(&s.mv_pivot[l]);
+            if (s.left[r] >= 0) count += __ldcg(&s.mv_pivot[r]);
+            s.mv_pivot[cur] = count;
+            __threadfence();
+            cur = s.parent[cur];
+            if (cur < 0) break;
+            if (atomicAdd(&s.mv_y[cur], 1) != 1) break;  // the other subtree is not finished yet
+        }
+    }
+    grid.sync();
+    for (int e = tid; e < ne; e += nthreads) {
+        int idx = e;
+        if (e < n_used) {
+            idx = 0;
+            for (int cur = e, guard = 0; s.parent[cur] >= 0 && guard < kReinsertMaxWalk; guard++) {
+                const int par = s.parent[cur];
+                idx += 1;
+                if (s.right[par] == cur && s.left[s.left[par]] >= 0) idx += __ldcg(&s.mv_pivot[s.left[par]]);
+                cur = par;
+            }
+        }
+        s.canon[e] = idx;
+    }
+    grid.sync();
+
     float my = 0;
     for (int i = tid; i < n_used; i += nthreads) my += reinsert_node_cost(v, i, kSahCostNode, kSahCostPrim);
     const float root_area = box_half_area(s.box[0]);
@@ -109,7 +153,7 @@ __global__ void __launch_bounds__(kRT) reinsert_kernel(DevTree t, ReinsertScratc
             ReinsertMove mv;
             int y = -1;
             if (reinsert_find(v, x, min_gain, mv)) {
-                const unsigned long long key = reinsert_key(round, mv.gain, x);
+                const unsigned long long key = reinsert_key(round, mv.gain, s.canon[x]);
                 if (reinsert_paths(v, x, mv.y, mv.pivot, [&](int n) { atomicMax(&s.lock[n], key); return true; })) {
                     y = mv.y;
                     s.mv_pivot[x] = mv.pivot;

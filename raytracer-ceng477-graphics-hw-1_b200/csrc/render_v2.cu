@@ -41,6 +41,9 @@ constexpr int kMaxP2 = 16;  // kAccShared: item side in pixels when f > 1 (acc s
 #ifndef RT_MIN_CTAS2
 #define RT_MIN_CTAS2 7
 #endif
+#ifndef RT_SKIP_ZERO_SPECULAR
+#define RT_SKIP_ZERO_SPECULAR 1  // A/B: 0 computes the specular term of materials without specular reflectance too
+#endif
 #ifndef RT_FORCE_EAGER_LOOP
 #define RT_FORCE_EAGER_LOOP 0  // A/B: run the refill loop (round 1's only shape) even at threshold 0
 #endif
@@ -223,7 +226,18 @@ RT_DEV bool trace_step(const RenderParams &p, Lane &L, const LaneStacks &S, V3 I
             const V3 wiReal = normalize(lpos - L.Pt);
             const float cosTheta = dot(wiReal, L.n);
             const V3 E = I / (dist * dist);
+#if RT_SKIP_ZERO_SPECULAR
+            // raytracer.cpp:411-418 with ks == (0, 0, 0): the term is (ks * pow(..)) (.) E = (+-0) (.) E, which is +-0 in every
+            // component when E is finite, and colour + (+-0) == colour bit for bit (colour is never -0: it starts as
+            // +0 + ambient).  pow() cannot make it NaN: its base is max(0, .) of two unit vectors' dot product (NaN -> 0 by
+            // std::max's operand order) and the exponent is checked on the host (scene_build.cu).  With a non-finite E
+            // (a light ON the surface point) the full path below runs.  On horse_and_mug this skips one normalisation, one
+            // pow and two loads for every unoccluded shadow ray from the floor.
+            const bool no_spec = (__float_as_int(m1.w) & 2) && (fabsf(E.x) + fabsf(E.y) + fabsf(E.z) <= FLT_MAX);
+            if (!no_spec && specular_gate(cosTheta)) {
+#else
             if (specular_gate(cosTheta)) {
+#endif
                 const float4 m2 = __ldg(&p.materials[4 * (L.mat - 1) + 2]);
                 const V3 h = normalize(wi + (-L.dn));
                 const float c = pow_ref(std_max(0.0f, dot(L.hitprim < p.n_tris ? xyz(__ldg(&p.tri_nn[L.hitprim])) : normalize(L.n), h)), m0.w);
@@ -248,7 +262,7 @@ RT_DEV bool trace_step(const RenderParams &p, Lane &L, const LaneStacks &S, V3 I
             cnt.shadow++;
         } else {
             const float4 m1 = __ldg(&p.materials[4 * (L.mat - 1) + 1]);
-            if (__float_as_int(m1.w) != 0) {  // mirror: raytracer.cpp:430-439
+            if (__float_as_int(m1.w) & 1) {  // mirror: raytracer.cpp:430-439
                 RT_CHECK(L.npush >= 0 && L.npush <= kMaxSupportedDepth);
                 S.local_stack[L.npush] = L.color;
                 S.mat_stack[L.npush] = L.mat;

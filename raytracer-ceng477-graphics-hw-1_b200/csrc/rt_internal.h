@@ -47,7 +47,7 @@ namespace rtb {
 //  ref_nodes  float4[3 * n_ref]     the reference's own tree: [0] = min.xyz bits(axis | is_leaf << 2)
 //                                   [1] = max.xyz bits(left child)  [2] = bits(first) bits(count) - -   (right child = left + 1)
 //  ref_leaf_prims int[n_prims]      prim ids in the reference's leaf order; slot_of_prim int[n_prims]; prim_bounds float4[2 * n_prims]
-//  materials  float4[4 * nm]        [0] = ka.xyz phong  [1] = kd.xyz bits(is_mirror)  [2] = ks.xyz 0  [3] = km.xyz 0
+//  materials  float4[4 * nm]        [0] = ka.xyz phong  [1] = kd.xyz bits(is_mirror | no_specular << 1)  [2] = ks.xyz 0  [3] = km.xyz 0
 //  lights     float4[2 * nl]        [0] = position.xyz  [1] = intensity.xyz
 // ---------------------------------------------------------------------------------------------
 

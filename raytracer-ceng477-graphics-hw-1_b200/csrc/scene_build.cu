@@ -448,6 +448,7 @@ void carve_scratch(Bump &b, Scratch &s, const RtSceneDesc &d, int builder, int p
         s.reinsert.key = b.take<unsigned long long>(ne);
         s.reinsert.mv_y = b.take<int>(ne);
         s.reinsert.mv_pivot = b.take<int>(ne);
+        s.reinsert.canon = b.take<int>(ne);
         s.reinsert.partial = b.take<float>(reinsert_grid);
         s.reinsert.counters = b.take<int>(reinsert_counter_slots());
     }
@@ -638,7 +639,11 @@ int SceneBuild::run(const RtSceneDesc &d, int builder, int ploc_radius, float pl
     for (int i = 0; i < d.n_materials; i++) {
         const RtMaterial &m = d.materials[i];
         mats[4 * (size_t) i + 0] = make_float4(m.ambient.x, m.ambient.y, m.ambient.z, m.phong_exponent);
-        mats[4 * (size_t) i + 1] = make_float4(m.diffuse.x, m.diffuse.y, m.diffuse.z, bits(m.is_mirror ? 1 : 0));
+        // bit 0: mirror; bit 1: the specular term of this material is exactly +-0 whatever the geometry (ks == 0 and an
+        // exponent for which pow() of a value in [0, 1 + 3e-7] stays finite) — render_v2.cu then skips computing it
+        const bool no_specular = m.specular.x == 0.0f && m.specular.y == 0.0f && m.specular.z == 0.0f && m.phong_exponent >= 0.0f &&
+                                 m.phong_exponent <= 1e6f;
+        mats[4 * (size_t) i + 1] = make_float4(m.diffuse.x, m.diffuse.y, m.diffuse.z, bits((m.is_mirror ? 1 : 0) | (no_specular ? 2 : 0)));
         mats[4 * (size_t) i + 2] = make_float4(m.specular.x, m.specular.y, m.specular.z, 0.f);
         mats[4 * (size_t) i + 3] = make_float4(m.mirror.x, m.mirror.y, m.mirror.z, 0.f);
     }

@@ -264,7 +264,7 @@ def golden_image(key):
 
 
 def random_scene(seed, n_tris=40, n_spheres=4, n_lights=2, max_depth=3, width=96, height=64, flat_fraction=0.3,
-                 camera_inside_sphere=False):
+                 camera_inside_sphere=False, zero_specular=False):
     """A seeded triangle/sphere soup with the hard cases mixed in: axis-aligned (zero-thickness) triangles, triangles
     sharing edges and vertices (exact-t ties), a degenerate triangle, mirrors, lights inside geometry."""
     rng = np.random.default_rng(seed)
@@ -305,6 +305,11 @@ def random_scene(seed, n_tris=40, n_spheres=4, n_lights=2, max_depth=3, width=96
     m13[:, 9:12] = rng.uniform(0, 0.9, (n_mat, 3))
     m13[:, 12] = rng.choice([1, 2, 3, 10, 50, 100, 2.5], n_mat)
     mirror = (rng.random(n_mat) < 0.5).astype(np.int32)
+    if zero_specular:  # materials whose specular term is exactly zero (the kernel skips computing it), one written as -0
+        m13[0:3, 6:9] = 0.0
+        m13[1, 6] = -0.0
+        m13[2, 12] = 0.0  # pow(x, 0) == 1: still a zero term
+        m13[3, 6:9] = [0.0, 0.5, 0.0]  # not ALL zero: the full path
     lights = np.zeros((n_lights, 6), np.float32)
     lights[:, 0:3] = rng.uniform(-6, 6, (n_lights, 3)) + np.array([0, 4, -6.0])
     lights[:, 3:6] = rng.uniform(200, 2000, (n_lights, 3))

@@ -196,6 +196,13 @@ def test_reinsertion_on_gpu_equals_host(scene):
     rt = H.RayTracer(sc, builder=H.rt_b200.RT_BUILD_SAH_GPU, reinsert_rounds=8, reinsert_accept=1e9)
     i = rt.info()
     rt.close()
+    for _ in range(3):  # node slots come from an atomic counter and differ from run to run; the result must not
+        rt = H.RayTracer(sc, builder=H.rt_b200.RT_BUILD_SAH_GPU, reinsert_rounds=8, reinsert_accept=1e9)
+        j = rt.info()
+        rt.close()
+        # (the cost is summed in slot order: equal up to rounding)
+        assert (j.reinsert_moves, j.reinsert_rounds, j.bvh_max_depth, j.bvh_nodes) == (i.reinsert_moves, i.reinsert_rounds, i.bvh_max_depth, i.bvh_nodes)
+        assert j.reinsert_cost_after == pytest.approx(i.reinsert_cost_after, rel=1e-5) and j.bvh_sah_cost == pytest.approx(i.bvh_sah_cost, rel=1e-5)
     print(scene, "host", list(cost), list(stats), "device", i.reinsert_cost_before, i.reinsert_cost_after, i.reinsert_moves, i.reinsert_rounds,
           "depth", i.bvh_max_depth, f"build {i.ms_build_device:.3f} ms")
     assert i.reinsert_moves == stats[0] and i.reinsert_rounds == stats[1] and i.bvh_max_depth == stats[2]
@@ -323,6 +330,25 @@ def test_seeded_scenes_against_oracle(seed):
             (ost.primary_rays, ost.reflection_rays, ost.shadow_rays, ost.shadow_occluded), (seed, aa, builder, refill)
         rt.close()
     oracle.close()
+
+
+@pytest.mark.parametrize("seed", range(300, 312))
+def test_zero_specular_materials_against_oracle(seed):
+    """Materials with ks = (0, 0, 0) (also -0, also exponent 0): the kernel skips their specular term — (+-0) (.) E added
+    to the colour — instead of computing it (render_v2.cu, RT_SKIP_ZERO_SPECULAR).  Must be invisible: frames and ray
+    counts equal the oracle's, with mirrors, spheres and lights inside geometry in the mix."""
+    sc = H.random_scene(seed, n_tris=40 + 5 * (seed % 7), n_spheres=seed % 5, max_depth=seed % 4, width=120, height=80, zero_specular=True)
+    cam = sc.camera(0)
+    aa = (1, 3, 8)[seed % 3]
+    oracle = H.OracleScene(sc)
+    want, ost = oracle.render(cam, aa)
+    oracle.close()
+    rt = H.RayTracer(sc)
+    got = rt.render(cam, aa)
+    st = rt.last_stats
+    rt.close()
+    assert np.array_equal(want, got), (seed, H.diff_report(want, got))
+    assert (st.primary_rays, st.reflection_rays, st.shadow_rays, st.shadow_occluded) == (ost.primary_rays, ost.reflection_rays, ost.shadow_rays, ost.shadow_occluded)
 
 
 @pytest.mark.parametrize("block", range(10))
