@@ -212,6 +212,7 @@ int g_band_rows = 0, g_strip_width = 0;
 // the copy engine, so it only pays when the kernel runs much longer than the transfer — 8K 16x: 655.9 -> 654.6 ms,
 // horse_and_mug 1440x720: 0.468 -> 0.446 ms, but simple 800x800: 0.104 -> 0.151 ms.
 long long g_zero_copy_min = 32LL << 20;
+constexpr int kZeroCopyPartAA = 8;  // rt_render_part_to_host / rt_render_multi: parts of frames supersampled at least this much
 
 ItemGeom item_geometry(const RtCamera *cam, int aa, int world) {
     ItemGeom g;
@@ -553,10 +554,25 @@ int render_part_common(RtScene *s, const RtCamera *cam, int aa, int rank, int wo
 // enqueue: this part's bands into the handle's packed buffer, then straight into the rows of a host frame
 int enqueue_part_to_host(RtScene *s, const RtCamera *cam, int aa, int rank, int world, unsigned char *host_frame, int *launches) {
     const ItemGeom g = item_geometry(cam, aa, world);
+    const int k = kControlSlots - 1;
+    // Heavily supersampled frame into a page-locked frame: the kernel stores its finished pixel runs straight into the
+    // frame's rows over this GPU's PCIe link, the transfer rides along with the rendering.  What decides is kernel time
+    // against transfer time, i.e. rays per output byte ~ aa^2, not the size of the part: at 16x16 the kernel runs ~100x
+    // longer than its 3 bytes per pixel take to cross PCIe (8 GPUs, 8K: 0.4 ms of copy after a 72 ms kernel saved).
+    void *alias = nullptr;
+    const bool zero_copy = g_zero_copy_min >= 0 && aa >= kZeroCopyPartAA && is_pinned(host_frame) &&
+                           cudaHostGetDevicePointer(&alias, host_frame, 0) == cudaSuccess && alias;
+    cudaGetLastError();
+    if (zero_copy) {
+        CU(cudaEventRecord(s->ev_part[0], s->stream));
+        int rc = enqueue_part(s, cam, aa, rank, world, (unsigned char *) alias, kOutFrame, k, s->stream, launches);
+        if (rc != RT_OK) return rc;
+        CU(cudaEventRecord(s->ev_part[1], s->stream));
+        return RT_OK;
+    }
     const size_t bytes = (size_t) part_bands(g, rank, world) * g.Ph * g.rpb * cam->image_width * 3;
     int rc = ensure(&s->d_parts, &s->parts_cap, bytes ? bytes : 1, false);
     if (rc != RT_OK) return rc;
-    const int k = kControlSlots - 1;
     CU(cudaEventRecord(s->ev_part[0], s->stream));
     rc = enqueue_part(s, cam, aa, rank, world, s->d_parts, kOutPacked, k, s->stream, launches);
     if (rc != RT_OK) return rc;
@@ -635,7 +651,7 @@ int rt_host_frame_create(const char *name, int64_t bytes, void **ptr) {
         return fail(RT_ERR_NOMEM, "mmap of the shared frame failed");
     }
     memset(p, 0, (size_t) bytes);  // touch every page before pinning
-    if (cudaHostRegister(p, (size_t) bytes, cudaHostRegisterPortable) != cudaSuccess) {
+    if (cudaHostRegister(p, (size_t) bytes, cudaHostRegisterPortable | cudaHostRegisterMapped) != cudaSuccess) {
         cudaGetLastError();
         munmap(p, (size_t) bytes);
         shm_unlink(name);
@@ -652,7 +668,7 @@ int rt_host_frame_open(const char *name, int64_t bytes, void **ptr) {
     void *p = mmap(nullptr, (size_t) bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
     close(fd);
     if (p == MAP_FAILED) return fail(RT_ERR_NOMEM, "mmap of the shared frame failed");
-    if (cudaHostRegister(p, (size_t) bytes, cudaHostRegisterPortable) != cudaSuccess) {
+    if (cudaHostRegister(p, (size_t) bytes, cudaHostRegisterPortable | cudaHostRegisterMapped) != cudaSuccess) {
         cudaGetLastError();
         munmap(p, (size_t) bytes);
         return fail(RT_ERR_CUDA, "cudaHostRegister of the shared frame failed");

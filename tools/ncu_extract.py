@@ -48,7 +48,8 @@ def main():
     def dram(k):
         return num(k, 0.0) * UNIT_SCALE.get(sel.get(k, {}).get("unit", "byte"), 1.0)
     summary = {"source": os.path.relpath(out, ROOT), "workload": key, "rays_in_launch": rays,
-               "kernel_ms": num("gpu__time_duration.sum", 0) / (1e6 if sel.get("gpu__time_duration.sum", {}).get("unit") in ("ns", "nsecond") else 1.0),
+               "kernel_ms": num("gpu__time_duration.sum", 0) / {"ns": 1e6, "nsecond": 1e6, "us": 1e3, "usecond": 1e3, "s": 1e-3, "second": 1e-3}.get(
+                   sel.get("gpu__time_duration.sum", {}).get("unit"), 1.0),
                "issue_slot_util": num("sm__issue_active.avg.pct_of_peak_sustained_elapsed"),
                "lanes_active": num("smsp__thread_inst_executed_pred_on_per_inst_executed.ratio"),
                "warp_inst_per_ray": num("smsp__inst_executed.sum", 0) / rays,
