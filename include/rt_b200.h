@@ -211,6 +211,9 @@ int rt_band_height(const RtCamera *cam, int aa_factor, int part_world);
 /* Tuning / experiments: overrides the band height (pixel rows) and the strip width of the 16x16-type kernel for the whole
  * process (0 = built-in defaults).  Every rank of a multi-process run must set the same values. */
 int rt_set_partition(int band_rows, int strip_width);
+/* Tuning / experiments: width in pixels (a power of two, 4..512) of the 1024-pixel blocks in which the 16x16-type kernel
+ * numbers a part's pixels (0 = built-in: 32). */
+int rt_set_block_width(int pixels);
 
 /* pixel rows part `part_rank` owns (its last band padded to the full band height), and bytes of its packed buffer
  * (rows * image_width * 3). */

@@ -214,6 +214,13 @@ int g_band_rows = 0, g_strip_width = 0;
 long long g_zero_copy_min = 32LL << 20;
 constexpr int kZeroCopyPartAA = 8;  // rt_render_part_to_host / rt_render_multi: parts of frames supersampled at least this much
 
+int g_block_width = 0;  // experiments (rt_set_block_width): 0 = block_width_log2()'s choice
+int block_width_log2(int world) {
+    if (g_block_width >= 4 && g_block_width <= 512) return 31 - __builtin_clz((unsigned) g_block_width);
+    (void) world;
+    return 5;  // 32 x 32 pixels.  Flatter blocks for multi-GPU parts (whose rows are `world` image rows apart) were tried: no gain
+}
+
 ItemGeom item_geometry(const RtCamera *cam, int aa, int world) {
     ItemGeom g;
     const int nx = cam->image_width, ny = cam->image_height;
@@ -299,7 +306,10 @@ int enqueue_part(RtScene *s, const RtCamera *cam, int aa, int rank, int world, u
     p.part_world = world;
     const long long n_groups = (p.n_bands + g.group_bands - 1) / g.group_bands;  // p.n_bands counts item rows
     // register-accumulator mode: the work counter runs over pixel slots in block order (32 rows x 32 pixels per block)
-    const long long n_items = g.acc_mode == 1 ? n_groups * ((cam->image_width + 31) / 32) * 1024
+    // (the block shape is a knob of tools/partition_experiment.py: rt_set_block_width)
+    p.blk_w_log2 = block_width_log2(world);
+    const int blk_w = 1 << p.blk_w_log2, blk_h = 1024 >> p.blk_w_log2;
+    const long long n_items = g.acc_mode == 1 ? (long long) ((p.n_bands + blk_h - 1) / blk_h) * ((cam->image_width + blk_w - 1) / blk_w) * 1024
                                               : n_groups * g.tiles_per_group * g.tile_items * g.group_bands;
     if (n_items >= (1LL << 32) - (1 << 22)) return fail(RT_ERR_INVALID, "too many work items");
     p.n_items = (unsigned) n_items;
@@ -325,7 +335,7 @@ int enqueue_part(RtScene *s, const RtCamera *cam, int aa, int rank, int world, u
     const long long need = (units + s->warps_per_cta - 1) / s->warps_per_cta;
     if (ctas > need) ctas = need;
     if (p.acc_mode == 1) {
-        p.tiles_per_group = (cam->image_width + 31) / 32;
+        p.tiles_per_group = (cam->image_width + blk_w - 1) / blk_w;
         p.guide = (unsigned) (4 * ctas * s->warps_per_cta);
     }
     const cudaError_t e = (cudaError_t) launch_render_v2(p, (int) ctas, stream);
@@ -610,6 +620,11 @@ int rt_warmup(int device) {
 
 // tuning: smallest frame (bytes) that rt_render / rt_render_async let the kernel write straight into a page-locked
 // destination; negative = always render into device memory and copy afterwards
+int rt_set_block_width(int pixels) {
+    g_block_width = pixels;
+    return RT_OK;
+}
+
 int rt_set_zero_copy(int64_t min_frame_bytes) {
     g_zero_copy_min = min_frame_bytes;
     return RT_OK;

@@ -50,6 +50,7 @@ struct RenderParams {
     int group_bands, tile_items, tiles_per_group;
     int part_rank, part_world;
     unsigned int n_items;  // work items of this part (incl. empty padding items); register-accumulator mode: pixel slots
+    int blk_w_log2;        // register-accumulator mode: pixel slots are numbered in blocks of 2^blk_w_log2 x 2^(10 - blk_w_log2) pixels
     unsigned int guide;    // register-accumulator mode: a warp claims ~ remaining / guide pixels at a time (4 x warps in flight)
     int out_mode;
     int refill_threshold;  // shared-accumulator mode: refill idle lanes once <= this many lanes are busy

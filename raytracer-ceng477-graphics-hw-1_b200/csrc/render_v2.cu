@@ -341,6 +341,7 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
         const int bpx = f >> 3, bpy = f >> 2;
         const unsigned ff = (unsigned) (f * f);
         const unsigned total = p.n_items, tiles_x = (unsigned) p.tiles_per_group;
+        const unsigned bw = (unsigned) p.blk_w_log2, bh = 10u - bw;  // block of 1024 pixel slots: 2^bw wide, 2^bh (local) rows high
         for (;;) {
             unsigned start = 0, n = 0;
             if (lane == 0) {
@@ -356,8 +357,8 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
             // lane i < n owns pixel start + i
             const unsigned idx = start + (unsigned) lane;
             const unsigned t = idx >> 10;
-            const int local_row = (int) ((t / tiles_x) * 32u + ((idx >> 5) & 31u));
-            const int x = (int) ((t % tiles_x) * 32u + (idx & 31u));
+            const int local_row = (int) (((t / tiles_x) << bh) + ((idx >> bw) & ((1u << bh) - 1u)));
+            const int x = (int) (((t % tiles_x) << bw) + (idx & ((1u << bw) - 1u)));
             // local row -> global row: bands of rows_per_band rows, band b of this part = part_rank + b * part_world
             const int y = (p.part_rank + (local_row / p.rows_per_band) * p.part_world) * p.rows_per_band + local_row % p.rows_per_band;
             const bool valid = lane < (int) n && local_row < p.n_bands && x < p.nx && y < p.ny;

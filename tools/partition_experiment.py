@@ -27,6 +27,17 @@ def part_ms(rank, n):
     return best
 
 
+if len(sys.argv) > 5 and sys.argv[5] == "blocks":  # block shape sweep (rt_set_block_width) at the default band height / run length
+    L.rt_set_block_width(32)
+    full = part_ms(0, 1)
+    for n in (1, 2, 4, world):
+        for bw in (32, 64, 128, 256):
+            L.rt_set_block_width(bw)
+            ms = [part_ms(r, n) for r in range(n)]
+            print(f"world {n} block {bw:3d}x{1024 // bw:<3d}: max {max(ms):.2f} mean {sum(ms) / n:.2f} ms; ideal {full / n:.2f}; "
+                  f"efficiency if the slowest part decides {full / n / max(ms):.4f}, mean part {full / n / (sum(ms) / n):.4f}", flush=True)
+    rt.close()
+    sys.exit(0)
 for strip in (0, 8, 4, 2):
     L.rt_set_partition(0, strip)
     full = part_ms(0, 1)
