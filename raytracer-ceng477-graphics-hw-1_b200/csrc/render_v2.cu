@@ -51,7 +51,9 @@ constexpr int kMaxP2 = 16;  // kAccShared: item side in pixels when f > 1 (acc s
 #define RT_FORCE_EAGER_LOOP 0  // A/B: run the refill loop (round 1's only shape) even at threshold 0
 #endif
 
-enum Phase : int { kIdle = 0, kClosest = 1, kShadow = 2 };
+// Lane::state: < 0 idle, 0 a closest-hit ray in flight, k > 0 the shadow ray towards light k - 1 (phase and light index
+// in one register)
+constexpr int kIdle = -1, kClosest = 0;
 enum AccMode : int { kAccShared = 0, kAccRegs = 1, kAccEager = 2 };
 
 RT_DEV V3 clamp3(V3 c) {  // Vec3f::clamp(0, FLT_MAX), raytracer.cpp:451
@@ -61,8 +63,8 @@ RT_DEV V3 clamp3(V3 c) {  // Vec3f::clamp(0, FLT_MAX), raytracer.cpp:451
 // per-lane path state (scalars only: the compiler keeps a struct in registers only if nothing in it is indexed
 // dynamically, so the three stacks live in separate local arrays — see LaneStacks)
 struct Lane {
-    int phase;
-    int depth, npush, light, mat, hitprim;
+    int state;
+    int depth, mat, hitprim;  // depth: reflection levels above this ray == levels pushed on the fold stacks
     V3 color, Pt, n, dn;
     Ray ray;
     float limit;
@@ -82,21 +84,20 @@ RT_DEV void start_primary(const RenderParams &p, Lane &L, V3 E0, V3 Q, V3 U, V3 
     L.ray = make_ray(E0, s - E0);
     L.limit = FLT_MAX;
     L.depth = 0;
-    L.npush = 0;
-    L.phase = kClosest;
+    L.state = kClosest;
 }
 
 // One ray per active lane through the BVH (closest-hit and any-hit share the loop), then the lane consumes its
 // result.  Returns true when the lane's path is finished; rgb then holds the quantised sample.
 template <bool FAR>
 RT_DEV bool trace_step(const RenderParams &p, Lane &L, const LaneStacks &S, V3 Ia, Counters &cnt, unsigned &r8, unsigned &g8, unsigned &b8) {
-    const int phase = L.phase;
-    const bool any = phase == kShadow;
+    const int state = L.state;
+    const bool any = state > 0;
     float tbest = L.limit;
     int pbest = -1;
     float tsecond = FLT_MAX;
     bool occluded = false;
-    if (phase != kIdle && p.n_nodes > 0) {
+    if (state >= 0 && p.n_nodes > 0) {
         if (p.brute_force) {
             for (int s = 0; s < p.n_prims && !occluded; s++) {
                 float t;
@@ -179,7 +180,7 @@ RT_DEV bool trace_step(const RenderParams &p, Lane &L, const LaneStacks &S, V3 I
     }
 
     // reference visibility: a doubtful hit is replayed on the reference's own tree (device_common.cuh)
-    if (p.exact_culling && phase != kIdle && pbest >= 0 && (p.exact_culling == 2 || !robust_visible(p, L.ray, pbest, tbest, any ? FLT_MAX : tsecond))) {
+    if (p.exact_culling && state >= 0 && pbest >= 0 && (p.exact_culling == 2 || !robust_visible(p, L.ray, pbest, tbest, any ? FLT_MAX : tsecond))) {
         if (any) {
             cnt.replay_any++;
             occluded = ref_any(p, L.ray, L.limit);
@@ -194,7 +195,8 @@ RT_DEV bool trace_step(const RenderParams &p, Lane &L, const LaneStacks &S, V3 I
     bool finish = false;
     V3 result = mk(0.0f, 0.0f, 0.0f);
 
-    if (phase == kClosest) {
+    int next_light = 0;
+    if (state == kClosest) {
         if (pbest < 0) {  // raytracer.cpp:442-449
             result = L.depth > 0 ? mk(0.0f, 0.0f, 0.0f) : ld3(p.background);
             finish = true;
@@ -213,15 +215,15 @@ RT_DEV bool trace_step(const RenderParams &p, Lane &L, const LaneStacks &S, V3 I
             L.Pt = L.ray.o + L.ray.d * tbest;
             L.hitprim = pbest;
             L.dn = normalize(L.ray.d);
-            L.light = 0;
             lights_done = p.n_lights == 0;
         }
-    } else if (phase == kShadow) {
+    } else if (state > 0) {
+        const int light = state - 1;
         if (occluded) {
             cnt.occluded++;
         } else {  // raytracer.cpp:406-423
-            const V3 lpos = xyz(__ldg(&p.lights[2 * L.light]));
-            const V3 I = xyz(__ldg(&p.lights[2 * L.light + 1]));
+            const V3 lpos = xyz(__ldg(&p.lights[2 * light]));
+            const V3 I = xyz(__ldg(&p.lights[2 * light + 1]));
             const float4 m0 = __ldg(&p.materials[4 * (L.mat - 1)]);
             const float4 m1 = __ldg(&p.materials[4 * (L.mat - 1) + 1]);
             const V3 wi = L.ray.d;
@@ -249,27 +251,26 @@ RT_DEV bool trace_step(const RenderParams &p, Lane &L, const LaneStacks &S, V3 I
             const float cd = std_max(0.0f, std_min(1.0f, cosTheta));
             L.color = L.color + mulv(xyz(m1) * cd, E);
         }
-        L.light++;
-        lights_done = L.light >= p.n_lights;
+        next_light = state;
+        lights_done = next_light >= p.n_lights;
     }
 
-    if (phase != kIdle && !finish) {
+    if (state >= 0 && !finish) {
         const V3 Pe = L.Pt + L.n * p.eps;  // raytracer.cpp:397
         if (!lights_done) {                // raytracer.cpp:399-404: shadow ray towards light `light`
-            const V3 lpos = xyz(__ldg(&p.lights[2 * L.light]));
+            const V3 lpos = xyz(__ldg(&p.lights[2 * next_light]));
             const V3 toL = lpos - Pe;
             const float dist = length(toL);
             L.ray = make_ray(Pe, toL / dist);
             L.limit = dist;
-            L.phase = kShadow;
+            L.state = next_light + 1;
             cnt.shadow++;
         } else {
             const float4 m1 = __ldg(&p.materials[4 * (L.mat - 1) + 1]);
             if (__float_as_int(m1.w) & 1) {  // mirror: raytracer.cpp:430-439
-                RT_CHECK(L.npush >= 0 && L.npush <= kMaxSupportedDepth);
-                S.local_stack[L.npush] = L.color;
-                S.mat_stack[L.npush] = L.mat;
-                L.npush++;
+                RT_CHECK(L.depth >= 0 && L.depth <= kMaxSupportedDepth);
+                S.local_stack[L.depth] = L.color;
+                S.mat_stack[L.depth] = L.mat;
                 const V3 nn = L.hitprim < p.n_tris ? xyz(__ldg(&p.tri_nn[L.hitprim])) : normalize(L.n);
                 const float rc = dot(-L.dn, nn);
                 L.depth++;
@@ -279,7 +280,7 @@ RT_DEV bool trace_step(const RenderParams &p, Lane &L, const LaneStacks &S, V3 I
                 } else {
                     L.ray = make_ray(Pe, L.dn + (nn * 2.0f) * rc);
                     L.limit = FLT_MAX;
-                    L.phase = kClosest;
+                    L.state = kClosest;
                     cnt.reflection++;
                 }
             } else {
@@ -290,14 +291,14 @@ RT_DEV bool trace_step(const RenderParams &p, Lane &L, const LaneStacks &S, V3 I
     }
 
     if (finish) {
-        int npush = L.npush;
+        int npush = L.depth;  // (a path cut off by the depth limit has pushed its last level too: depth was incremented)
         while (npush > 0) {  // fold the mirror levels back to front
             npush--;
             const V3 km = xyz(__ldg(&p.materials[4 * (S.mat_stack[npush] - 1) + 3]));
             result = clamp3(S.local_stack[npush] + mulv(result, km));
         }
         r8 = quantise(result.x), g8 = quantise(result.y), b8 = quantise(result.z);
-        L.phase = kIdle;
+        L.state = kIdle;
     }
     return finish;
 }
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
             // local row -> global row: bands of rows_per_band rows, band b of this part = part_rank + b * part_world
             const int y = (p.part_rank + (local_row / p.rows_per_band) * p.part_world) * p.rows_per_band + local_row % p.rows_per_band;
             const bool valid = lane < (int) n && local_row < p.n_bands && x < p.nx && y < p.ny;
-            L.phase = kIdle;
+            L.state = kIdle;
             unsigned mine = 0u;  // B << 16 | G << 8 | R of this lane's pixel
             for (int pix = 0; pix < (int) n; pix++) {
                 if (!__shfl_sync(0xffffffffu, (int) valid, pix)) continue;
@@ -380,7 +381,7 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
                         do {
                             unsigned r8, g8, b8;
                             if (trace_step<FAR>(p, L, S, Ia, cnt, r8, g8, b8)) rgb = r8 | (g8 << 8) | (b8 << 16);
-                        } while (__any_sync(0xffffffffu, L.phase != kIdle));
+                        } while (__any_sync(0xffffffffu, L.state >= 0));
                         tr += __reduce_add_sync(0xffffffffu, rgb & 0xffu);
                         tg += __reduce_add_sync(0xffffffffu, (rgb >> 8) & 0xffu);
                         tb += __reduce_add_sync(0xffffffffu, rgb >> 16);
@@ -397,7 +398,7 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
                         do {
                             unsigned r8, g8, b8;
                             if (trace_step<FAR>(p, L, S, Ia, cnt, r8, g8, b8)) sr += r8, sg += g8, sb += b8;
-                        } while (__any_sync(0xffffffffu, L.phase != kIdle));
+                        } while (__any_sync(0xffffffffu, L.state >= 0));
                     }
                 }
                 // raytracer.cpp:475-477: truncating integer average of the quantised sub-samples
@@ -442,7 +443,7 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
         const int pw = min(P, p.nx - px0);
         const int ph = min(p.Ph, p.ny - py0);
         if (pw <= 0 || ph <= 0) continue;
-        L.phase = kIdle;
+        L.state = kIdle;
         {
             // ---- P x Ph pixels, sub-samples in 8x4 blocks, lanes refilled from the item ------------------------
             unsigned *acc = acc_all + (threadIdx.x >> 5) * (P * p.Ph * 3);
@@ -479,7 +480,7 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
                     do {
                         unsigned r8, g8, b8;
                         if (trace_step<FAR>(p, L, S, Ia, cnt, r8, g8, b8)) sample_done(lx, ly, r8, g8, b8);
-                    } while (__any_sync(0xffffffffu, L.phase != kIdle));
+                    } while (__any_sync(0xffffffffu, L.state >= 0));
                 }
             } else {
                 // kAccEager (experiments, RtBuildOptions.refill_threshold > 0): idle lanes are refilled with the item's next
@@ -489,11 +490,11 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
                 int next = 0;        // warp-uniform: next unassigned slot of this item
                 int lx = 0, ly = 0;  // the lane's sub-sample within the item
                 for (;;) {
-                    const unsigned idle_mask = __ballot_sync(0xffffffffu, L.phase == kIdle);
+                    const unsigned idle_mask = __ballot_sync(0xffffffffu, L.state < 0);
                     if (idle_mask != 0u && next < total && 32 - __popc(idle_mask) <= p.refill_threshold) {
                         const int my = next + __popc(idle_mask & lt_mask);
                         next += __popc(idle_mask);
-                        if (L.phase == kIdle && my < total) {
+                        if (L.state < 0 && my < total) {
                             const int b = my >> 5, l = my & 31;
                             lx = (b % nbx) * 8 + (l & 7);
                             ly = (b / nbx) * 4 + (l >> 3);
@@ -503,7 +504,7 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
                             }
                         }
                     }
-                    if (idle_mask == 0xffffffffu && __ballot_sync(0xffffffffu, L.phase != kIdle) == 0u) {
+                    if (idle_mask == 0xffffffffu && __ballot_sync(0xffffffffu, L.state >= 0) == 0u) {
                         if (next >= total) break;
                         continue;
                     }
