@@ -304,6 +304,16 @@ def test_single_process_multi_gpu():
     assert rc == 0, L.rt_last_error()
     assert np.array_equal(out, single)
     assert (st.primary_rays, st.reflection_rays, st.shadow_rays) == (want.primary_rays, want.reflection_rays, want.shadow_rays)
+    # AA factor 8 and up: every GPU's kernel stores its finished pixels straight into the page-locked frame (the caller's, or
+    # the library's staging frame when the caller's memory is pageable) instead of copying its bands afterwards
+    cam8 = sc.camera(0, 350, 190)
+    single8 = tracer("horse_and_mug").render(cam8, 8)
+    out8 = np.zeros_like(single8)
+    assert L.rt_render_multi(arr, n, C.byref(cam8), 8, out8.ctypes.data, C.byref(st)) == 0, L.rt_last_error()
+    assert np.array_equal(out8, single8)
+    pinned = torch.zeros(single8.size, dtype=torch.uint8).pin_memory()
+    assert L.rt_render_multi(arr, n, C.byref(cam8), 8, C.c_void_p(pinned.data_ptr()), C.byref(st)) == 0, L.rt_last_error()
+    assert np.array_equal(pinned.numpy().reshape(single8.shape), single8)
     for h in handles:
         h.close()
 
