@@ -177,6 +177,23 @@ def test_reinsertion_keeps_the_tree_valid_and_never_raises_its_cost(scene):
     assert s8[2] <= 60 and s16[2] <= 60
 
 
+@pytest.mark.parametrize("seed", range(40, 52))
+def test_reinsertion_on_seeded_soups(seed):
+    """The same on seeded triangle / sphere soups full of awkward boxes: zero-thickness (axis-aligned) triangles, a
+    degenerate triangle, a big floor quad, spheres, shared edges — areas of 0, equal boxes, ties in the gains."""
+    L = H.rt_b200.cuda_lib()
+    L.rt_host_reinsert.argtypes = [C.POINTER(H.RtSceneDesc), C.c_int, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
+    sc = H.random_scene(seed, n_tris=60 + 40 * (seed % 5), n_spheres=seed % 7, flat_fraction=0.15 * (seed % 6))
+    prev = None
+    for rounds in (0, 1, 8, 30):
+        cost, stats = (C.c_float * 2)(), (C.c_int32 * 4)()
+        n = L.rt_host_reinsert(C.byref(sc.desc), rounds, 1e9, cost, stats)
+        assert n >= 1, L.rt_last_error()
+        assert cost[1] <= cost[0] * (1 + 1e-6) and stats[2] <= 60 and stats[1] <= max(rounds, 0)
+        assert prev is None or cost[1] <= prev * (1 + 1e-5)
+        prev = cost[1]
+
+
 def test_reinsertion_repairs_the_floor_of_horse_and_mug():
     """The case it exists for (tools/tree_lab.cpp): the top-down builder carries the two floor triangles deep into the
     hierarchy (SAH cost 7.19); eight rounds move them to the root (4.38, below PLOC's 4.44) — node steps per ray on the
