@@ -47,6 +47,11 @@ constexpr int kMaxP2 = 16;  // kAccShared: item side in pixels when f > 1 (acc s
 #ifndef RT_ROUND_REDUX
 #define RT_ROUND_REDUX 1  // A/B: 0 keeps three per-lane colour sums across the rounds of a pixel
 #endif
+#ifndef RT_RELOAD_HIT
+#define RT_RELOAD_HIT 1  // the hit's normal and material are re-read from the primitive id (one 128-bit load) whenever a lane
+                         // consumes a ray, instead of living in four registers across the traversals: car -4 %, the other
+                         // scenes -0.3..-0.7 % (A/B: 0)
+#endif
 #ifndef RT_FORCE_EAGER_LOOP
 #define RT_FORCE_EAGER_LOOP 0  // A/B: run the refill loop (round 1's only shape) even at threshold 0
 #endif
@@ -64,8 +69,12 @@ RT_DEV V3 clamp3(V3 c) {  // Vec3f::clamp(0, FLT_MAX), raytracer.cpp:451
 // dynamically, so the three stacks live in separate local arrays — see LaneStacks)
 struct Lane {
     int state;
-    int depth, mat, hitprim;  // depth: reflection levels above this ray == levels pushed on the fold stacks
-    V3 color, Pt, n, dn;
+    int depth, hitprim;  // depth: reflection levels above this ray == levels pushed on the fold stacks
+    V3 color, Pt, dn;
+#if !RT_RELOAD_HIT
+    int mat;
+    V3 n;
+#endif
     Ray ray;
     float limit;
 };
@@ -74,6 +83,7 @@ struct LaneStacks {
     V3 *local_stack;  // [kMaxSupportedDepth + 1]
     int *mat_stack;   // [kMaxSupportedDepth + 1]
     int *stack;       // [kStackSize] traversal stack
+    float *sph_n;     // [3] RT_RELOAD_HIT: the normal of a hit sphere (a triangle's is re-read from tri_nm)
 };
 
 RT_DEV void start_primary(const RenderParams &p, Lane &L, V3 E0, V3 Q, V3 U, V3 Vv, int sx, int sy) {
@@ -196,6 +206,22 @@ RT_DEV bool trace_step(const RenderParams &p, Lane &L, const LaneStacks &S, V3 I
     V3 result = mk(0.0f, 0.0f, 0.0f);
 
     int next_light = 0;
+    V3 n = mk(0.0f, 0.0f, 0.0f);  // normal and material of the surface this lane is shading
+    int mat = 1;
+#if RT_RELOAD_HIT
+    if (state > 0) {
+        if (L.hitprim < p.n_tris) {
+            const float4 nm = __ldg(&p.tri_nm[L.hitprim]);
+            n = xyz(nm);
+            mat = __float_as_int(nm.w);
+        } else {
+            n = mk(S.sph_n[0], S.sph_n[1], S.sph_n[2]);
+            mat = __ldg(&p.sph_mat[L.hitprim - p.n_tris]);
+        }
+    }
+#else
+    if (state > 0) n = L.n, mat = L.mat;
+#endif
     if (state == kClosest) {
         if (pbest < 0) {  // raytracer.cpp:442-449
             result = L.depth > 0 ? mk(0.0f, 0.0f, 0.0f) : ld3(p.background);
@@ -203,14 +229,20 @@ RT_DEV bool trace_step(const RenderParams &p, Lane &L, const LaneStacks &S, V3 I
         } else {
             if (pbest < p.n_tris) {
                 const float4 nm = __ldg(&p.tri_nm[pbest]);
-                L.n = xyz(nm);
-                L.mat = __float_as_int(nm.w);
+                n = xyz(nm);
+                mat = __float_as_int(nm.w);
             } else {
                 const float4 cr = __ldg(&p.sph_cr[pbest - p.n_tris]);
-                L.mat = __ldg(&p.sph_mat[pbest - p.n_tris]);
-                L.n = normalize((((L.ray.o + L.ray.d * tbest) - xyz(cr)) / cr.w));  // raytracer.cpp:91
+                mat = __ldg(&p.sph_mat[pbest - p.n_tris]);
+                n = normalize((((L.ray.o + L.ray.d * tbest) - xyz(cr)) / cr.w));  // raytracer.cpp:91
+#if RT_RELOAD_HIT
+                S.sph_n[0] = n.x, S.sph_n[1] = n.y, S.sph_n[2] = n.z;
+#endif
             }
-            const float4 m0 = __ldg(&p.materials[4 * (L.mat - 1)]);
+#if !RT_RELOAD_HIT
+            L.n = n, L.mat = mat;
+#endif
+            const float4 m0 = __ldg(&p.materials[4 * (mat - 1)]);
             L.color = mk(0.0f, 0.0f, 0.0f) + mulv(xyz(m0), Ia);  // raytracer.cpp:394-395
             L.Pt = L.ray.o + L.ray.d * tbest;
             L.hitprim = pbest;
@@ -224,12 +256,12 @@ RT_DEV bool trace_step(const RenderParams &p, Lane &L, const LaneStacks &S, V3 I
         } else {  // raytracer.cpp:406-423
             const V3 lpos = xyz(__ldg(&p.lights[2 * light]));
             const V3 I = xyz(__ldg(&p.lights[2 * light + 1]));
-            const float4 m0 = __ldg(&p.materials[4 * (L.mat - 1)]);
-            const float4 m1 = __ldg(&p.materials[4 * (L.mat - 1) + 1]);
+            const float4 m0 = __ldg(&p.materials[4 * (mat - 1)]);
+            const float4 m1 = __ldg(&p.materials[4 * (mat - 1) + 1]);
             const V3 wi = L.ray.d;
             const float dist = L.limit;
             const V3 wiReal = normalize(lpos - L.Pt);
-            const float cosTheta = dot(wiReal, L.n);
+            const float cosTheta = dot(wiReal, n);
             const V3 E = I / (dist * dist);
 #if RT_SKIP_ZERO_SPECULAR
             // raytracer.cpp:411-418 with ks == (0, 0, 0): the term is (ks * pow(..)) (.) E = (+-0) (.) E, which is +-0 in every
@@ -243,9 +275,9 @@ RT_DEV bool trace_step(const RenderParams &p, Lane &L, const LaneStacks &S, V3 I
 #else
             if (specular_gate(cosTheta)) {
 #endif
-                const float4 m2 = __ldg(&p.materials[4 * (L.mat - 1) + 2]);
+                const float4 m2 = __ldg(&p.materials[4 * (mat - 1) + 2]);
                 const V3 h = normalize(wi + (-L.dn));
-                const float c = pow_ref(std_max(0.0f, dot(L.hitprim < p.n_tris ? xyz(__ldg(&p.tri_nn[L.hitprim])) : normalize(L.n), h)), m0.w);
+                const float c = pow_ref(std_max(0.0f, dot(L.hitprim < p.n_tris ? xyz(__ldg(&p.tri_nn[L.hitprim])) : normalize(n), h)), m0.w);
                 L.color = L.color + mulv(xyz(m2) * c, E);
             }
             const float cd = std_max(0.0f, std_min(1.0f, cosTheta));
@@ -256,7 +288,7 @@ RT_DEV bool trace_step(const RenderParams &p, Lane &L, const LaneStacks &S, V3 I
     }
 
     if (state >= 0 && !finish) {
-        const V3 Pe = L.Pt + L.n * p.eps;  // raytracer.cpp:397
+        const V3 Pe = L.Pt + n * p.eps;  // raytracer.cpp:397
         if (!lights_done) {                // raytracer.cpp:399-404: shadow ray towards light `light`
             const V3 lpos = xyz(__ldg(&p.lights[2 * next_light]));
             const V3 toL = lpos - Pe;
@@ -266,12 +298,12 @@ RT_DEV bool trace_step(const RenderParams &p, Lane &L, const LaneStacks &S, V3 I
             L.state = next_light + 1;
             cnt.shadow++;
         } else {
-            const float4 m1 = __ldg(&p.materials[4 * (L.mat - 1) + 1]);
+            const float4 m1 = __ldg(&p.materials[4 * (mat - 1) + 1]);
             if (__float_as_int(m1.w) & 1) {  // mirror: raytracer.cpp:430-439
                 RT_CHECK(L.depth >= 0 && L.depth <= kMaxSupportedDepth);
                 S.local_stack[L.depth] = L.color;
-                S.mat_stack[L.depth] = L.mat;
-                const V3 nn = L.hitprim < p.n_tris ? xyz(__ldg(&p.tri_nn[L.hitprim])) : normalize(L.n);
+                S.mat_stack[L.depth] = mat;
+                const V3 nn = L.hitprim < p.n_tris ? xyz(__ldg(&p.tri_nn[L.hitprim])) : normalize(n);
                 const float rc = dot(-L.dn, nn);
                 L.depth++;
                 if (L.depth > p.max_depth) {  // raytracer.cpp:387-389
@@ -330,7 +362,8 @@ __global__ void __launch_bounds__(kThreads2, RT_MIN_CTAS2) render_kernel_v2(cons
     V3 local_stack[kMaxSupportedDepth + 1];
     int mat_stack[kMaxSupportedDepth + 1];
     int stack[kStackSize];
-    const LaneStacks S = {local_stack, mat_stack, stack};
+    float sph_n[3];
+    const LaneStacks S = {local_stack, mat_stack, stack, sph_n};
 
     if (ACC == kAccRegs) {
         // ---- f = 8 * bpx = 4 * bpy: strips of up to 32 pixels of one row, GUIDED self-scheduling ---------------------
