@@ -770,6 +770,69 @@ int main(int argc, char **argv) {
             evaluate_host(nm, h);
         }
     }
+    if (getenv("LAB_PROBE")) {
+        // Could the builder CHOOSE between candidate trees by measurement instead of by SAH cost, without knowing the camera?
+        // Probe rays a scene offers at creation time: from random surface points (area-weighted) to every light (what shadow
+        // rays are), one random direction off each point (reflections), and from a sphere around the scene to random surface
+        // points (primary rays of some camera).  Below: node steps per probe ray next to the steps per ray of the scene's own
+        // camera — if the two rank the candidates alike, a few thousand probe rays on the device can replace the 0.8x rule.
+        auto probe = [&](HostBvh bvh, double *per_kind) {
+            pad_boxes(bvh, bounds);
+            Sim sim(bvh, tris);
+            std::vector<double> cdf(nt);
+            double acc = 0;
+            for (int i = 0; i < nt; i++) {
+                V c = cross(tris[i].b - tris[i].a, tris[i].c - tris[i].a);
+                acc += 0.5 * std::sqrt(dot(c, c));
+                cdf[i] = acc;
+            }
+            unsigned long long rng = 0x9E3779B97F4A7C15ull;
+            auto uni = [&]() { rng ^= rng << 13, rng ^= rng >> 7, rng ^= rng << 17; return (double) (rng >> 11) / 9007199254740992.0; };
+            Aabb sb = empty_box();
+            for (auto &b: bounds) sb = merge(sb, b);
+            V ctr{0.5 * (sb.mn[0] + sb.mx[0]), 0.5 * (sb.mn[1] + sb.mx[1]), 0.5 * (sb.mn[2] + sb.mx[2])};
+            double rad = 0;
+            for (int k = 0; k < 3; k++) rad += (double) (sb.mx[k] - sb.mn[k]) * (sb.mx[k] - sb.mn[k]);
+            rad = std::sqrt(rad);  // sphere of twice the scene's radius
+            Stats st[3];
+            for (int it = 0; it < 4000 && nt > 0; it++) {
+                int i = (int) (std::lower_bound(cdf.begin(), cdf.end(), uni() * acc) - cdf.begin());
+                if (i >= nt) i = nt - 1;
+                double u = uni(), v = uni();
+                if (u + v > 1) u = 1 - u, v = 1 - v;
+                const Tri &T = tris[i];
+                V P = T.a + (T.b - T.a) * u + (T.c - T.a) * v, Pe = P + T.n * (double) d.shadow_ray_epsilon;
+                double t;
+                for (int li = 0; li < d.n_lights; li++) {
+                    V lp{d.lights[li].position.x, d.lights[li].position.y, d.lights[li].position.z}, toL = lp - Pe;
+                    double dist = std::sqrt(dot(toL, toL));
+                    sim.trace(Pe, toL * (1.0 / dist), true, dist, t, st[2]);
+                }
+                V dir{uni() * 2 - 1, uni() * 2 - 1, uni() * 2 - 1};
+                if (dot(dir, T.n) < 0) dir = dir * -1.0;
+                sim.trace(Pe, norm(dir), false, DBL_MAX, t, st[1]);
+                V dd = norm(V{uni() * 2 - 1, uni() * 2 - 1, uni() * 2 - 1});
+                V eye = ctr + dd * rad;
+                sim.trace(eye, P - eye, false, DBL_MAX, t, st[0]);
+            }
+            double all_steps = 0, all_rays = 0;
+            for (int k = 0; k < 3; k++) per_kind[k] = st[k].steps / std::max(1.0, st[k].rays), all_steps += st[k].steps, all_rays += st[k].rays;
+            return all_steps / std::max(1.0, all_rays);
+        };
+        HostBvh plain, opt, pl = to_host(build_ploc(bounds, 16));
+        build_bvh_sah_host_plain(bounds, plain);
+        build_bvh_sah_host_plain(bounds, opt);
+        reinsert_optimize_host(opt, 8, 1e9f);
+        const char *names[3] = {"top-down as built", "top-down + 8 rounds", "ploc r16"};
+        HostBvh *cands[3] = {&plain, &opt, &pl};
+        for (int c = 0; c < 3; c++) {
+            double k[3];
+            double all = probe(*cands[c], k);
+            printf("probe rays  %-22s sah %6.3f | steps/ray %6.3f  (outside-in %.3f, off-surface %.3f, to-lights %.3f)\n", names[c], cands[c]->sah_cost, all, k[0], k[1], k[2]);
+            evaluate_host(names[c], *cands[c]);
+        }
+        return 0;
+    }
     if (getenv("LAB_LIBRARY_ONLY")) return 0;
     for (int variant = 0; variant < 3; variant++) {
         BTree *base = variant == 0 ? &ploc : &binned;
